@@ -1,0 +1,304 @@
+"""Benchmark of the Zephyr hypothesis-scoring hot path (BASELINE.json metric: hypotheses scored/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4]
+                    [--precision bf16|fp32]
+
+A "step" is one pass of the hot path over one synthetic frame: for every object, project the model
+points under every pose hypothesis, gather, featurise, score with the MLP, take the per-object top-k
+(and, for N>1, all-gather the k candidates).  N=1 workload = BASELINE.json configs[1]
+(YCB-V-shaped frame, 21 objects x 10,000 hypotheses x 1,000 points).  For N>1 every rank keeps
+that per-GPU load (weak scaling): objects carry 10,000*N hypotheses, sharded contiguously.
+
+One JSON line on stdout (rank 0).  `value` = whole-job hypotheses/s with inputs resident in HBM;
+`e2e` = the same through the public host-buffer API (H2D of frame, clouds and poses and D2H of the
+top-k inside the timed region).  `--impl reference` times the CPU restatement of the reference
+path (oracle/, torch CPU, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # name: (intrinsics, n_obj, hypotheses per object per GPU, points per object, description)
+    "c1": ("lmo", 1, 1000, 1000, "synthetic 640x480, 1 object x 1,000 hypotheses x 1,000 pts"),
+    "c2": ("ycbv", 21, 10000, 1000, "YCB-V-shaped frame: 21 objects x 10,000 hypotheses x 1,000 pts"),
+    "c3": ("lmo", 8, 50000, 1000, "LM-O-shaped frame: 8 objects x 50,000 hypotheses x 1,000 pts"),
+    "c4": ("hd", 1, 200000, 4000, "bandwidth stress: 1280x720, 1 object x 200,000 hypotheses x 4,000 pts"),
+}
+MLP_MACS_PER_POINT = 8 * 64 + 64 * 128 + 128 * 1024
+HEAD_MACS = 1024 * 512 + 512 * 256 + 256
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def make_workload(name, n_gpus, seed=1):
+    """Synthetic frame for `name`; hypotheses per object scale with the GPU count (weak scaling)."""
+    from ossid_code_b200 import synthetic as syn
+    intr, n_obj, per_gpu, n_pts, _ = WORKLOADS[name]
+    sc = syn.make_scene(seed, intr, n_obj=n_obj, n_pts=n_pts, n_hypo=min(per_gpu, 10000))
+    reps = -(-per_gpu * n_gpus // min(per_gpu, 10000))
+    rng = np.random.default_rng(seed + 99)
+    for ob in sc["objects"]:
+        if reps > 1:   # more hypotheses of the same mixture, freshly drawn
+            extra = [syn.make_hypotheses(rng, ob["gt_pose"], min(per_gpu, 10000), sc["cam_K"], sc["H"], sc["W"])
+                     for _ in range(reps - 1)]
+            ob["pose_hypos"] = np.concatenate([ob["pose_hypos"], *extra])[: per_gpu * n_gpus]
+    return sc
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        out, _ = self.proc.communicate(timeout=10)
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(sample, n_repeat):
+    """Time the reference-style CPU path: our mirror of networkInference driving the torch-CPU oracle
+    objects, span = featurise + score as the reference defines it (zephyr_utils.py:29-37)."""
+    from oracle import zephyr_oracle as zo
+    from ossid_code_b200 import weights, zephyr_utils as glue
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ds, model = zo.OracleScoreDataset(100.0), zo.OracleScorer(weights.seeded_folded(0))
+    times, n_scored = [], 0
+    for _ in range(n_repeat):
+        data = dict(sample)
+        data["pose_hypos"] = sample["pose_hypos"].copy()
+        poses, scores, _, _, dt = glue.networkInference(model, ds, data, return_time=True)
+        times.append(dt)
+        n_scored = len(scores)
+    return times, n_scored, cores
+
+
+def cpu_sample(sc, n_hypo):
+    ob = sc["objects"][0]
+    return dict(img=sc["img"], depth=sc["depth"], cam_K=sc["cam_K"], model_points=ob["model_points"],
+                model_colors=ob["model_colors"], model_normals=ob["model_normals"],
+                pose_hypos=ob["pose_hypos"][:n_hypo])
+
+
+def run_reference(args):
+    """--impl reference: CPU restatement on a bounded sample of the same workload; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    intr, n_obj, per_gpu, n_pts, desc = WORKLOADS[args.workload]
+    sc = make_workload(args.workload, 1)
+    n_s = min(args.cpu_sample, per_gpu)
+    sample = cpu_sample(sc, n_s)
+    cpu_reference_run(sample, max(args.warmup, 1) if args.warmup else 0)
+    times, n_scored, cores = cpu_reference_run(sample, args.steps)
+    total = sum(times)
+    value = n_scored * len(times) / total
+    sample_desc = f"{n_s} hypotheses x {n_pts} pts of object 0 per step ({desc}), oracle port, torch CPU fp32"
+    line = {
+        "impl": "reference", "metric": "hypotheses_scored_per_sec", "value": value, "unit": "hypotheses/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "sample": sample_desc},
+        "cpu_baseline": {"value": value, "unit": "hypotheses/s", "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--k", type=int, default=8)
+    ap.add_argument("--cpu-sample", type=int, default=1000, help="hypotheses in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from ossid_code_b200 import scoring, weights
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if args.warmup < 3:
+        args.warmup = 3
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    intr, n_obj, per_gpu, n_pts, desc = WORKLOADS[args.workload]
+    sc = make_workload(args.workload, world)
+    w = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    fs = scoring.FrameScorer(w, device=local, precision=args.precision, inconst_ratio_th=100.0, k=args.k)
+    weight_of = (lambda o: o % 2)          # two scorers keyed on object parity, online_learning.py:461-463
+    total_hyp = sum(len(ob["pose_hypos"]) for ob in sc["objects"])
+    local_hyp = sum(scoring.shard_range(len(ob["pose_hypos"]), rank, world)[1]
+                    - scoring.shard_range(len(ob["pose_hypos"]), rank, world)[0] for ob in sc["objects"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm: `value` ------------------------------------------------------------
+    fs.upload(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of)
+    for _ in range(args.warmup):
+        S, I = fs.run_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    fs.stage_events = []
+    l0 = fs.ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        S, I = fs.run_resident()
+    e1.record()
+    barrier()
+    launches = fs.ctx.launches - l0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    stages = fs.stage_times_ms()
+    fs.stage_events = None
+    ms_step = ms_total / args.steps
+    value = total_hyp / (ms_step * 1e-3)
+
+    # ---- end-to-end arm through the public host-buffer API: `e2e` ----------------------------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    host_objs = [dict(model_points=pin(ob["model_points"]), model_colors=pin(ob["model_colors"]),
+                      model_normals=pin(ob["model_normals"]),
+                      pose_hypos=pin(ob["pose_hypos"].astype(np.float32))) for ob in sc["objects"]]
+    img_h, dep_h = pin(sc["img"]), pin(sc["depth"])
+    for _ in range(2):
+        fs.score_frame(img_h, dep_h, sc["cam_K"], host_objs, weight_of)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Sh, Ih = fs.score_frame(img_h, dep_h, sc["cam_K"], host_objs, weight_of)
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    h2d = img_h.numel() + dep_h.numel() * 4 + sum(3 * ob["model_points"].numel() * 4 for ob in host_objs) + local_hyp * 48
+    d2h = int(Sh.size * 4 + Ih.size * 4)
+
+    # ---- roofline of the dominant kernel + the feature kernel --------------------------------------
+    peaks = load_peaks()
+    fbytes = 2 if args.precision == "bf16" else 4
+    roof = {}
+    if "pool" in stages:
+        st = stages["pool"]
+        flops = 2.0 * MLP_MACS_PER_POINT * st["units"]
+        ach = flops / (st["ms"] * 1e-3) / 1e12
+        peak = peaks["tensor_sustained"]
+        roof["roofline"] = {"kernel": "zs_pool (shared MLP 8-64-128-1024 + max-pool)", "bound": "tensor",
+                            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                            "peak_source": peaks["source"] + ", sustained bf16", "launch_groups": st["calls"],
+                            "ms_in_timed_region": st["ms"], "share_of_step": st["ms"] / (ms_step * args.steps)}
+    if "features" in stages:
+        st = stages["features"]
+        hyp_units = st["units"] / n_pts
+        byts = hyp_units * (48 + n_pts * (8 * fbytes))       # poses in + features out (mask/uv not written on this path)
+        ach = byts / (st["ms"] * 1e-3) / 1e9
+        roof["roofline_features"] = {"kernel": "zs_features (projection + gather + residual features)", "bound": "hbm",
+                                     "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                                     "traffic": None, "peak_source": peaks["source"], "launch_groups": st["calls"],
+                                     "ms_in_timed_region": st["ms"], "share_of_step": st["ms"] / (ms_step * args.steps)}
+    if "head" in stages:
+        roof["head_share_of_step"] = stages["head"]["ms"] / (ms_step * args.steps)
+
+    line = {
+        "metric": "hypotheses_scored_per_sec", "value": value, "unit": "hypotheses/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "hypotheses_per_step": total_hyp, "objects": n_obj,
+                   "points_per_object": n_pts, "topk": args.k, "inconst_ratio_th": 100.0,
+                   "parallelism": f"hypothesis-sharded x{world}, one all-gather of top-k" if world > 1 else "single GPU",
+                   "l2": "feature chunks of 32768 hypotheses x 1000 pts (>= 0.5 GB) exceed the 126 MB L2; no flush needed",
+                   "weights": "seeded random (no checkpoint is published)"},
+        "e2e": {"value": total_hyp / e2e_s, "unit": "hypotheses/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    line.update(roof)
+
+    if rank == 0 and not args.no_cpu_baseline:
+        n_s = min(args.cpu_sample, per_gpu)
+        sample = cpu_sample(sc, n_s)
+        cpu_reference_run(sample, 1)
+        times, n_scored, cores = cpu_reference_run(sample, 3)
+        line["cpu_baseline"] = {"value": n_scored / statistics.median(times), "unit": "hypotheses/s", "cores": cores,
+                                "kind": "port",
+                                "sample": f"{n_s} hypotheses x {n_pts} pts of object 0, median of 3 (oracle port, torch CPU fp32)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define ZS_API __attribute__((visibility("default")))
+#else
+#define ZS_API
+#endif
+
 typedef struct zs_ctx zs_ctx;
 
 typedef enum {
@@ -56,17 +62,17 @@ enum { ZS_F32 = 0, ZS_BF16 = 1 };
 #define ZS_BIT_FREE_SPACE  8
 #define ZS_BIT_OCCLUDED    16
 
-int zs_version(void);
-const char* zs_strerror(int status);
+ZS_API int zs_version(void);
+ZS_API const char* zs_strerror(int status);
 
 /* Context life cycle.  Stands behind `ScoreDataset([], "", name, args, mode='test')` and
  * `PointNet2SSG(dim_point, args, num_class=1).to(0).eval()`
  * (python/ossid/scripts/online_learning.py:206-227). */
-int zs_create(zs_ctx** out, int device);
-void zs_destroy(zs_ctx* ctx);
-const char* zs_last_error(const zs_ctx* ctx);
+ZS_API int zs_create(zs_ctx** out, int device);
+ZS_API void zs_destroy(zs_ctx* ctx);
+ZS_API const char* zs_last_error(const zs_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
-int64_t zs_launch_count(const zs_ctx* ctx);
+ZS_API int64_t zs_launch_count(const zs_ctx* ctx);
 
 /* Frame upload.  Replaces the tensors built at python/ossid/utils/zephyr_utils.py:13-17.
  * zs_set_frame: rgb [dev] float32 H*W*3 in [0,1] (already blurred and divided by 255),
@@ -74,64 +80,71 @@ int64_t zs_launch_count(const zs_ctx* ctx);
  * camera; when blur != 0 the 5x5 Gaussian of cv2.GaussianBlur(img,(5,5),0) is applied on
  * the GPU with cv2's 8-bit fixed-point arithmetic before the /255.
  * Both pack {depth/camera_scale, H, S, V} per pixel into a context-owned frame. */
-int zs_set_frame(zs_ctx* ctx, const float* rgb, const float* depth, int H, int W,
+ZS_API int zs_set_frame(zs_ctx* ctx, const float* rgb, const float* depth, int H, int W,
                  float fx, float fy, float cx, float cy, float camera_scale, void* stream);
-int zs_set_frame_u8(zs_ctx* ctx, const uint8_t* img, const float* depth, int H, int W,
+ZS_API int zs_set_frame_u8(zs_ctx* ctx, const uint8_t* img, const float* depth, int H, int W,
                     float fx, float fy, float cx, float cy, float camera_scale, int blur, void* stream);
 
 /* Model cloud upload: pts/cols/nrms [dev] float32 (n_pts,3).  Replaces model_points /
  * model_colors / model_normals of the scoring dict (zephyr_utils.py:18-20). */
-int zs_set_object(zs_ctx* ctx, int slot, const float* pts, const float* cols, const float* nrms,
+ZS_API int zs_set_object(zs_ctx* ctx, int slot, const float* pts, const float* cols, const float* nrms,
                   int n_pts, void* stream);
 
 /* Scorer weights: blob [dev] float32, ZS_WEIGHT_FLOATS values = W1 b1 W2 b2 W3 b3 F1 c1 F2 c2
  * F3 c3 (BatchNorm folded), each weight (out,in) row-major.  Replaces
  * `model.load_state_dict(ckpt['state_dict'])` (online_learning.py:213-214). */
-int zs_set_weights(zs_ctx* ctx, int slot, const float* blob, size_t n_floats, void* stream);
+ZS_API int zs_set_weights(zs_ctx* ctx, int slot, const float* blob, size_t n_floats, void* stream);
 
 /* `zephyr.utils.projectPointsUv(pose_hypos, model_points, meta_data)`
  * (used at zephyr_utils.py:58): raw rounded pixel indices, no z or bounds test.
  * uv_out [dev] int32 [n][n_pts][2], [..,0]=x/col, [..,1]=y/row. */
-int zs_project_uv(zs_ctx* ctx, const float* poses, int n, const float* pts, int n_pts,
+ZS_API int zs_project_uv(zs_ctx* ctx, const float* poses, int n, const float* pts, int n_pts,
                   float fx, float fy, float cx, float cy, int32_t* uv_out, void* stream);
 
 /* Fused `filterHypoByMask` (zephyr_utils.py:49-71): per hypothesis, the number of model
  * points that project inside the frame onto a non-zero mask pixel.  mask [dev] uint8 H*W.
  * count_out [dev] int32 [n].  The caller applies `count / n_pts > th`. */
-int zs_mask_count(zs_ctx* ctx, const float* poses, int n, const float* pts, int n_pts,
+ZS_API int zs_mask_count(zs_ctx* ctx, const float* poses, int n, const float* pts, int n_pts,
                   float fx, float fy, float cx, float cy, const uint8_t* mask, int H, int W,
                   int32_t* count_out, void* stream);
 
 /* First half of `ScoreDataset.getPointNetData` (call site zephyr_utils.py:31): number of
  * free-space-violating points per hypothesis.  viol_out [dev] int32 [n]. */
-int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, int32_t* viol_out, void* stream);
+ZS_API int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, int32_t* viol_out, void* stream);
 
 /* Hypothesis pre-filter of getPointNetData (its effect is visible at zephyr_utils.py:39-43;
  * thresholds online_learning.py:174,184): keep h iff viol[h]*100/n_pts < th (th >= 100
  * keeps all); never empty (first minimum kept).  keep_idx_out [dev] int32 [n] ascending,
  * n_keep_out [dev] int32[1]. */
-int zs_filter(zs_ctx* ctx, const int32_t* viol, int n, int n_pts, float inconst_ratio_th,
+ZS_API int zs_filter(zs_ctx* ctx, const int32_t* viol, int n, int n_pts, float inconst_ratio_th,
               int32_t* keep_idx_out, int32_t* n_keep_out, void* stream);
 
 /* Second half of getPointNetData: features for hypotheses keep_idx[0..n_keep) of `poses`
  * (keep_idx NULL = all of 0..n_keep).  feat_out [dev] [n_keep][n_pts][8] float32 or bf16;
  * uv_out [dev] int32 [n_keep][n_pts][2] (nullable); mask_out [dev] uint8 [n_keep][n_pts]
  * (nullable); viol_out [dev] int32 [n_keep] (nullable). */
-int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const int32_t* keep_idx, int n_keep,
+ZS_API int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const int32_t* keep_idx, int n_keep,
                 void* feat_out, int feat_dtype, int32_t* uv_out, uint8_t* mask_out,
                 int32_t* viol_out, void* stream);
 
 /* Scorer forward, `model({"point_x": point_x})` (zephyr_utils.py:34).  feat [dev]
  * [n][n_pts][8] in feat_dtype.  precision ZS_F32: CUDA-core fp32 path (feat float32);
  * ZS_BF16: tcgen05 tensor-core path (feat bf16).  scores_out [dev] float32 [n]. */
-int zs_score(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtype, int n, int n_pts,
+ZS_API int zs_score(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtype, int n, int n_pts,
              int precision, float* scores_out, void* stream);
+
+/* The two halves of zs_score, exposed so that callers can keep the pooled vectors and so that
+ * each stage can be timed alone: zs_pool = shared per-point MLP + max over points
+ * (pooled_out [dev] float32 [n][1024]); zs_head = 1024 -> 512 -> 256 -> 1 (fp32). */
+ZS_API int zs_pool(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtype, int n, int n_pts,
+            float* pooled_out, void* stream);
+ZS_API int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n, float* scores_out, void* stream);
 
 /* Per-object top-k, ordered by (score desc, index asc); k <= ZS_MAX_TOPK.  Generalises
  * `scores.argmax()` (online_learning.py:466-467; first maximum wins ties).
  * s_out [dev] float32 [k], i_out [dev] int32 [k] (= local index + index_base); entries
  * beyond n are (-inf, -1). */
-int zs_topk(zs_ctx* ctx, const float* scores, int n, int k, int index_base,
+ZS_API int zs_topk(zs_ctx* ctx, const float* scores, int n, int k, int index_base,
             float* s_out, int32_t* i_out, void* stream);
 
 #ifdef __cplusplus

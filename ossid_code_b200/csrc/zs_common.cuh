@@ -1,0 +1,153 @@
+// Shared internals of libzs.so: context, error plumbing, exact-arithmetic device helpers.
+// Public ABI: include/zs.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/zs.h"
+
+#define ZS_DEPTH_MARGIN 0.02f   // metres; reference: python/ossid/datasets/ycbv_sift_dataset.py:325
+
+struct zs_frame {
+    float4* packed = nullptr;   // H*W x {depth/camera_scale, H, S, V}
+    size_t cap_px = 0;
+    int H = 0, W = 0;
+    float fx = 0, fy = 0, cx = 0, cy = 0, inv_fx = 0, inv_fy = 0;
+    bool set = false;
+};
+
+struct zs_object {
+    // {px,py,pz,Hm}, {nx,ny,nz,Sm}, Vm  -- 36 B per model point
+    float4* pA = nullptr;
+    float4* pB = nullptr;
+    float* pV = nullptr;
+    int n_pts = 0, cap = 0;
+};
+
+struct zs_weights {
+    float* f32 = nullptr;            // ZS_WEIGHT_FLOATS, layout of zs_set_weights
+    float* f32t = nullptr;           // transposed ([K][CO]) copies of W1 W2 W3 F1 F2 (zs_score_f32.cu)
+    __nv_bfloat16* bf16 = nullptr;   // tensor-core operand images of W1..W3 (see zs_score_tc.cu)
+    bool set = false;
+};
+
+struct zs_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int64_t launches = 0;
+    char err[512] = {0};
+    zs_frame frame;
+    zs_object obj[ZS_MAX_OBJECTS];
+    zs_weights w[ZS_MAX_WEIGHT_SLOTS];
+    float* lut255 = nullptr;         // i/255 as fp64 division rounded to fp32, i = 0..255 (zephyr_utils.py:14)
+    void* ws = nullptr;              // scratch (pooled vectors and the head's hidden layers)
+    size_t ws_bytes = 0;
+    void* tc_state = nullptr;        // owned by zs_score_tc.cu (tensor maps etc.)
+};
+
+// offsets (in floats) into the weight blob
+enum : int {
+    ZS_OFF_W1 = 0, ZS_OFF_B1 = ZS_OFF_W1 + 64 * 8,
+    ZS_OFF_W2 = ZS_OFF_B1 + 64, ZS_OFF_B2 = ZS_OFF_W2 + 128 * 64,
+    ZS_OFF_W3 = ZS_OFF_B2 + 128, ZS_OFF_B3 = ZS_OFF_W3 + 1024 * 128,
+    ZS_OFF_F1 = ZS_OFF_B3 + 1024, ZS_OFF_C1 = ZS_OFF_F1 + 512 * 1024,
+    ZS_OFF_F2 = ZS_OFF_C1 + 512, ZS_OFF_C2 = ZS_OFF_F2 + 256 * 512,
+    ZS_OFF_F3 = ZS_OFF_C2 + 256, ZS_OFF_C3 = ZS_OFF_F3 + 256,
+    ZS_OFF_END = ZS_OFF_C3 + 1
+};
+static_assert(ZS_OFF_END == ZS_WEIGHT_FLOATS, "weight blob layout");
+
+int zs_fail(zs_ctx* ctx, int code, const char* fmt, ...);
+int zs_reserve_ws(zs_ctx* ctx, size_t bytes);
+int zs_tc_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);   // zs_score_tc.cu
+void zs_tc_destroy(zs_ctx* ctx);
+int zs_score_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, int n_pts, float* pooled, cudaStream_t st);
+int zs_f32_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);  // zs_score_f32.cu
+
+#define ZS_CUDA(ctx, call)                                                                      \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return zs_fail((ctx), ZS_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,      \
+                           cudaGetErrorString(e_));                                             \
+    } while (0)
+
+#define ZS_LAUNCHED(ctx)                                                                        \
+    do {                                                                                        \
+        (ctx)->launches++;                                                                      \
+        cudaError_t e_ = cudaGetLastError();                                                    \
+        if (e_ != cudaSuccess)                                                                  \
+            return zs_fail((ctx), ZS_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__,         \
+                           cudaGetErrorString(e_));                                             \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Exact arithmetic.  The oracle performs one IEEE fp32 operation per step in a fixed order;
+// the intrinsics below are never contracted into FMAs by nvcc, whatever -fmad says.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// ((r0*px + r1*py) + r2*pz) [+ t]
+__device__ __forceinline__ float xdot3(float r0, float r1, float r2, float px, float py, float pz) {
+    return xadd(xadd(xmul(r0, px), xmul(r1, py)), xmul(r2, pz));
+}
+
+// Hexcone RGB -> HSV, H in [0,1).  Same operation order as oracle/zephyr_oracle.py:rgb_to_hsv.
+__device__ __forceinline__ void zs_rgb_to_hsv(float r, float g, float b, float& h, float& s, float& v) {
+    float mx = fmaxf(fmaxf(r, g), b);
+    float mn = fminf(fminf(r, g), b);
+    float df = xsub(mx, mn);
+    float dfs = df > 0.f ? df : 1.f;
+    float hh;
+    if (mx == r) {
+        hh = xdiv(xsub(g, b), dfs);
+        if (hh < 0.f) hh = xadd(hh, 6.f);
+    } else if (mx == g) {
+        hh = xadd(xdiv(xsub(b, r), dfs), 2.f);
+    } else {
+        hh = xadd(xdiv(xsub(r, g), dfs), 4.f);
+    }
+    h = df > 0.f ? xdiv(hh, 6.f) : 0.f;
+    s = mx > 0.f ? xdiv(df, mx) : 0.f;
+    v = mx;
+}
+
+struct zs_cam {
+    float fx, fy, cx, cy, inv_fx, inv_fy;
+    int H, W;
+};
+
+struct zs_pose {
+    float r[12];
+};
+
+__device__ __forceinline__ zs_pose zs_load_pose(const float* __restrict__ poses, int h) {
+    zs_pose p;
+    const float4* q = reinterpret_cast<const float4*>(poses + (size_t)h * 12);
+    float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    p.r[0] = a.x; p.r[1] = a.y; p.r[2] = a.z; p.r[3] = a.w;
+    p.r[4] = b.x; p.r[5] = b.y; p.r[6] = b.z; p.r[7] = b.w;
+    p.r[8] = c.x; p.r[9] = c.y; p.r[10] = c.z; p.r[11] = c.w;
+    return p;
+}
+
+// R.p + t with the oracle's association.
+__device__ __forceinline__ void zs_transform(const zs_pose& T, float px, float py, float pz,
+                                             float& x, float& y, float& z) {
+    x = xadd(xdot3(T.r[0], T.r[1], T.r[2], px, py, pz), T.r[3]);
+    y = xadd(xdot3(T.r[4], T.r[5], T.r[6], px, py, pz), T.r[7]);
+    z = xadd(xdot3(T.r[8], T.r[9], T.r[10], px, py, pz), T.r[11]);
+}
+
+// Rounded (float-valued) pixel coordinates, (x/z)*f + c, round-half-even.
+__device__ __forceinline__ void zs_project(const zs_cam& cam, float x, float y, float z, float& ur, float& vr) {
+    ur = rintf(xadd(xmul(xdiv(x, z), cam.fx), cam.cx));
+    vr = rintf(xadd(xmul(xdiv(y, z), cam.fy), cam.cy));
+}

@@ -1,0 +1,424 @@
+// Kernel 1 family: projection, gather, per-point residual features, masks, violation counts,
+// hypothesis pre-filter, raw uv projection, mask-overlap count.  ABI: include/zs.h.
+//
+// Mapping (all kernels here): one WARP owns one hypothesis at a time; lanes stride over the
+// model points, so every per-point store is a contiguous, fully coalesced warp store
+// (features: 32 lanes x 32 B fp32 or 16 B bf16; mask: 32 x 1 B; uv: 32 x 8 B).  The pose sits in
+// registers, the model cloud (36 B/point) in shared memory, the packed frame (16 B/pixel, a few
+// MB) is gathered through the read-only path and lives in L1/L2.  Grids are a multiple of the
+// SM count; warps walk the hypothesis list with a grid stride.
+//
+// Everything that decides an integer or a mask bit uses the non-contractable intrinsics of
+// zs_common.cuh in the oracle's order; the remaining float features may use FMA / MUFU.
+#include "zs_common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+
+struct obj_view {
+    const float4* pA;
+    const float4* pB;
+    const float* pV;
+    int n_pts;
+};
+
+__device__ __forceinline__ void st_cs_f4(float4* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cs_u4(uint4* p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// Stage the model cloud into shared memory (or leave it in global when it does not fit).
+template <bool kSmem>
+__device__ __forceinline__ void stage_cloud(const obj_view& o, float4*& sA, float4*& sB, float*& sV, char* smem) {
+    if (kSmem) {
+        sA = reinterpret_cast<float4*>(smem);
+        sB = sA + o.n_pts;
+        sV = reinterpret_cast<float*>(sB + o.n_pts);
+        for (int i = threadIdx.x; i < o.n_pts; i += blockDim.x) {
+            sA[i] = __ldg(o.pA + i);
+            sB[i] = __ldg(o.pB + i);
+            sV[i] = __ldg(o.pV + i);
+        }
+        __syncthreads();
+    } else {
+        sA = const_cast<float4*>(o.pA);
+        sB = const_cast<float4*>(o.pB);
+        sV = const_cast<float*>(o.pV);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Features.  kBf16: feature dtype.  kSmem: model cloud staged in shared memory.
+// ---------------------------------------------------------------------------------------
+template <bool kBf16, bool kSmem>
+__global__ void __launch_bounds__(kThreads)
+zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
+              const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out,
+              int32_t* __restrict__ uv_out, uint8_t* __restrict__ mask_out, int32_t* __restrict__ viol_out) {
+    extern __shared__ __align__(16) char smem[];
+    float4 *sA, *sB;
+    float* sV;
+    stage_cloud<kSmem>(o, sA, sB, sV, smem);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerCta;
+    const int N = o.n_pts;
+    const float fW = (float)cam.W, fH = (float)cam.H;
+
+    for (int hk = warp; hk < n_keep; hk += n_warps) {
+        const int h = keep_idx ? __ldg(keep_idx + hk) : hk;
+        const zs_pose T = zs_load_pose(poses, h);
+        const size_t row = (size_t)hk * N;
+        int viol = 0;
+        for (int p0 = 0; p0 < N; p0 += 32) {
+            const int p = p0 + lane;
+            const bool act = p < N;
+            uint32_t mk = 0;
+            float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f, f5 = 0.f, f6 = 0.f;
+            int ui = 0, vi = 0;
+            if (act) {
+                const float4 a = kSmem ? sA[p] : __ldg(sA + p);
+                const float4 b = kSmem ? sB[p] : __ldg(sB + p);
+                const float vm = kSmem ? sV[p] : __ldg(sV + p);
+                float x, y, z, ur, vr;
+                zs_transform(T, a.x, a.y, a.z, x, y, z);
+                zs_project(cam, x, y, z, ur, vr);
+                const bool valid = (z > 0.f) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
+                // R.n, same association as the points (no translation)
+                const float nx = xdot3(T.r[0], T.r[1], T.r[2], b.x, b.y, b.z);
+                const float ny = xdot3(T.r[4], T.r[5], T.r[6], b.x, b.y, b.z);
+                const float nz = xdot3(T.r[8], T.r[9], T.r[10], b.x, b.y, b.z);
+                const float dot = -xadd(xadd(xmul(x, nx), xmul(y, ny)), xmul(z, nz));
+                mk = dot > 0.f ? ZS_BIT_FRONT : 0;
+                if (valid) {
+                    ui = (int)ur;
+                    vi = (int)vr;
+                    const float4 px = __ldg(frame + (size_t)vi * cam.W + ui);   // {d_obs, H, S, V}
+                    const bool vd = px.x > 0.f;
+                    const float dD = vd ? xsub(px.x, z) : 0.f;
+                    mk |= ZS_BIT_VALID_PROJ | (vd ? ZS_BIT_VALID_DEPTH : 0);
+                    if (vd && dD > ZS_DEPTH_MARGIN) mk |= ZS_BIT_FREE_SPACE;
+                    if (vd && dD < -ZS_DEPTH_MARGIN) mk |= ZS_BIT_OCCLUDED;
+                    float dH = px.y - a.w;
+                    dH = dH > 0.5f ? dH - 1.0f : dH;
+                    dH = dH < -0.5f ? dH + 1.0f : dH;
+                    f0 = ((float)ui - cam.cx) * cam.inv_fx;
+                    f1 = ((float)vi - cam.cy) * cam.inv_fy;
+                    f2 = dH;
+                    f3 = px.z - b.w;
+                    f4 = px.w - vm;
+                    f5 = dD;
+                    // cos of the angle between the viewing ray and the rotated normal
+                    // (python/ossid/datasets/ycbv_object.py:74); 1e-4 feature, so rsqrt is fine
+                    const float q = (x * x + y * y + z * z) * (nx * nx + ny * ny + nz * nz);
+                    const float c = dot * rsqrtf(q);
+                    f6 = (c == c) ? c : 0.f;
+                }
+            }
+            viol += __popc(__ballot_sync(0xffffffffu, (mk & ZS_BIT_FREE_SPACE) != 0));
+            if (act) {
+                if (kBf16) {
+                    uint4 v;
+                    v.x = pack_bf16x2(f0, f1); v.y = pack_bf16x2(f2, f3);
+                    v.z = pack_bf16x2(f4, f5); v.w = pack_bf16x2(f6, 0.f);
+                    st_cs_u4(reinterpret_cast<uint4*>(feat_out) + row + p, v);
+                } else {
+                    float4* dst = reinterpret_cast<float4*>(feat_out) + (row + p) * 2;
+                    st_cs_f4(dst, make_float4(f0, f1, f2, f3));
+                    st_cs_f4(dst + 1, make_float4(f4, f5, f6, 0.f));
+                }
+                if (mask_out) mask_out[row + p] = (uint8_t)mk;
+                if (uv_out) reinterpret_cast<int2*>(uv_out)[row + p] = make_int2(ui, vi);
+            }
+        }
+        if (viol_out && lane == 0) viol_out[hk] = viol;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Violation count only (pre-filter pass): exact part of the feature kernel, depth gather only.
+// ---------------------------------------------------------------------------------------
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads)
+zs_k_violations(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
+                int n, int32_t* __restrict__ viol_out) {
+    extern __shared__ __align__(16) char smem[];
+    float4 *sA, *sB;
+    float* sV;
+    stage_cloud<kSmem>(o, sA, sB, sV, smem);
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerCta;
+    const int N = o.n_pts;
+    const float fW = (float)cam.W, fH = (float)cam.H;
+    const float* frame_d = reinterpret_cast<const float*>(frame);
+    for (int h = warp; h < n; h += n_warps) {
+        const zs_pose T = zs_load_pose(poses, h);
+        int viol = 0;
+        for (int p0 = 0; p0 < N; p0 += 32) {
+            const int p = p0 + lane;
+            bool fs = false;
+            if (p < N) {
+                const float4 a = kSmem ? sA[p] : __ldg(sA + p);
+                float x, y, z, ur, vr;
+                zs_transform(T, a.x, a.y, a.z, x, y, z);
+                zs_project(cam, x, y, z, ur, vr);
+                if ((z > 0.f) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH)) {
+                    const float d = __ldg(frame_d + 4 * ((size_t)(int)vr * cam.W + (int)ur));
+                    fs = (d > 0.f) && (xsub(d, z) > ZS_DEPTH_MARGIN);
+                }
+            }
+            viol += __popc(__ballot_sync(0xffffffffu, fs));
+        }
+        if (lane == 0) viol_out[h] = viol;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Raw projection (projectPointsUv) and mask-overlap count (filterHypoByMask).  Model points
+// come straight from the caller's (n_pts,3) float32 array.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int raw_round(float f) {
+    // non-finite or |f| >= 2^30 -> -2^30 (always outside any frame), as oracle project_raw
+    return (fabsf(f) < 1073741824.f) ? (int)f : -1073741824;
+}
+
+template <bool kCount>
+__global__ void __launch_bounds__(kThreads)
+zs_k_project(const float* __restrict__ poses, int n, const float* __restrict__ pts, int n_pts, zs_cam cam,
+             int32_t* __restrict__ uv_out, const uint8_t* __restrict__ mask, int32_t* __restrict__ count_out) {
+    extern __shared__ __align__(16) char smem[];
+    float* sp = reinterpret_cast<float*>(smem);
+    for (int i = threadIdx.x; i < 3 * n_pts; i += blockDim.x) sp[i] = __ldg(pts + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerCta;
+    for (int h = warp; h < n; h += n_warps) {
+        const zs_pose T = zs_load_pose(poses, h);
+        int cnt = 0;
+        for (int p0 = 0; p0 < n_pts; p0 += 32) {
+            const int p = p0 + lane;
+            bool in = false;
+            if (p < n_pts) {
+                float x, y, z, ur, vr;
+                zs_transform(T, sp[3 * p], sp[3 * p + 1], sp[3 * p + 2], x, y, z);
+                zs_project(cam, x, y, z, ur, vr);
+                const int u = raw_round(ur), v = raw_round(vr);
+                if (kCount) {
+                    // bounds predicate of python/ossid/utils/zephyr_utils.py:61-62
+                    const bool invalid = (v >= cam.H) || (v < 0) || (u >= cam.W) || (u < 0);
+                    in = !invalid && (__ldg(mask + (size_t)v * cam.W + u) != 0);
+                } else {
+                    reinterpret_cast<int2*>(uv_out)[(size_t)h * n_pts + p] = make_int2(u, v);
+                }
+            }
+            if (kCount) cnt += __popc(__ballot_sync(0xffffffffu, in));
+        }
+        if (kCount && lane == 0) count_out[h] = cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Hypothesis pre-filter: stable compaction of {h : viol[h]*100/n_pts < th}; single CTA.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+zs_k_filter(const int32_t* __restrict__ viol, int n, float n_pts_f, float th, int32_t* __restrict__ keep_idx,
+            int32_t* __restrict__ n_keep_out) {
+    __shared__ int s_warp[32];
+    __shared__ int s_total;
+    __shared__ unsigned long long s_min;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_min = ~0ull;
+    int base_out = 0;                  // kept so far (same value in every thread)
+    unsigned long long best = ~0ull;   // (viol << 32 | index): minimum = first minimum-violation hypothesis
+    for (int base = 0; base < n; base += 1024) {
+        const int h = base + threadIdx.x;
+        bool keep = false;
+        if (h < n) {
+            const int v = viol[h];
+            keep = (th >= 100.f) || (xdiv(xmul((float)v, 100.f), n_pts_f) < th);
+            const unsigned long long key = ((unsigned long long)(uint32_t)v << 32) | (uint32_t)h;
+            best = key < best ? key : best;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();               // previous iteration's readers of s_warp / s_total are done
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        if (wid == 0) {
+            const int c = s_warp[lane];
+            int incl = c;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            s_warp[lane] = incl - c;   // exclusive prefix over warps
+            if (lane == 31) s_total = incl;
+        }
+        __syncthreads();
+        if (keep) keep_idx[base_out + s_warp[wid] + __popc(bal & ((1u << lane) - 1u))] = h;
+        base_out += s_total;
+    }
+    for (int d = 16; d; d >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, d);
+        best = t < best ? t : best;
+    }
+    if (lane == 0) atomicMin(&s_min, best);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nk = base_out;
+        if (nk == 0 && n > 0) {        // never empty
+            keep_idx[0] = (int)(s_min & 0xffffffffull);
+            nk = 1;
+        }
+        *n_keep_out = nk;
+    }
+}
+
+int grid_for(const zs_ctx* ctx, int n, int ctas_per_sm) {
+    int need = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    int full = ctx->sm_count * ctas_per_sm;
+    if (need >= full) return full;
+    return need < 1 ? 1 : need;
+}
+
+constexpr size_t kCloudSmemMax = 200 * 1024;
+
+template <typename K>
+int opt_in_smem(zs_ctx* ctx, K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        ZS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return ZS_OK;
+}
+
+int check_obj(zs_ctx* ctx, int slot, const float* poses, obj_view& o, zs_cam& cam) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (slot < 0 || slot >= ZS_MAX_OBJECTS || ctx->obj[slot].n_pts == 0)
+        return zs_fail(ctx, ZS_ERR_STATE, "object slot %d not set", slot);
+    if (!ctx->frame.set) return zs_fail(ctx, ZS_ERR_STATE, "frame not set");
+    if (!poses || ((uintptr_t)poses & 15)) return zs_fail(ctx, ZS_ERR_INVALID, "poses must be non-null, 16-byte aligned");
+    const zs_object& ob = ctx->obj[slot];
+    o = obj_view{ob.pA, ob.pB, ob.pV, ob.n_pts};
+    const zs_frame& f = ctx->frame;
+    cam = zs_cam{f.fx, f.fy, f.cx, f.cy, f.inv_fx, f.inv_fy, f.H, f.W};
+    return ZS_OK;
+}
+
+}  // namespace
+
+extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const int32_t* keep_idx, int n_keep,
+                           void* feat_out, int feat_dtype, int32_t* uv_out, uint8_t* mask_out,
+                           int32_t* viol_out, void* stream) {
+    obj_view o;
+    zs_cam cam;
+    int rc = check_obj(ctx, obj_slot, poses, o, cam);
+    if (rc) return rc;
+    if (n_keep < 0 || (feat_dtype != ZS_F32 && feat_dtype != ZS_BF16))
+        return zs_fail(ctx, ZS_ERR_INVALID, "n_keep %d, feat_dtype %d", n_keep, feat_dtype);
+    if (n_keep == 0) return ZS_OK;
+    if (!feat_out || ((uintptr_t)feat_out & 15) || (uv_out && ((uintptr_t)uv_out & 7)))
+        return zs_fail(ctx, ZS_ERR_INVALID, "feat_out must be 16-byte aligned (uv_out 8)");
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t smem = (size_t)o.n_pts * 36;
+    const bool in_smem = smem <= kCloudSmemMax;
+    const int ctas_per_sm = in_smem ? (int)max((size_t)1, min((size_t)4, (220 * 1024) / (smem + 1024))) : 4;
+    const int grid = grid_for(ctx, n_keep, ctas_per_sm);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float4* frame = ctx->frame.packed;
+#define ZS_LAUNCH_FEAT(BF, SM)                                                                          \
+    do {                                                                                                \
+        rc = opt_in_smem(ctx, zs_k_features<BF, SM>, SM ? smem : 0);                                    \
+        if (rc) return rc;                                                                              \
+        zs_k_features<BF, SM><<<grid, kThreads, SM ? smem : 0, st>>>(o, cam, frame, poses, keep_idx,    \
+                                                                     n_keep, feat_out, uv_out, mask_out, viol_out); \
+    } while (0)
+    if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_FEAT(true, true); else ZS_LAUNCH_FEAT(true, false); }
+    else                       { if (in_smem) ZS_LAUNCH_FEAT(false, true); else ZS_LAUNCH_FEAT(false, false); }
+#undef ZS_LAUNCH_FEAT
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
+extern "C" int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, int32_t* viol_out, void* stream) {
+    obj_view o;
+    zs_cam cam;
+    int rc = check_obj(ctx, obj_slot, poses, o, cam);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && !viol_out)) return zs_fail(ctx, ZS_ERR_INVALID, "n %d", n);
+    if (n == 0) return ZS_OK;
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t smem = (size_t)o.n_pts * 36;
+    const bool in_smem = smem <= kCloudSmemMax;
+    const int ctas_per_sm = in_smem ? (int)max((size_t)1, min((size_t)4, (220 * 1024) / (smem + 1024))) : 4;
+    const int grid = grid_for(ctx, n, ctas_per_sm);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_smem) {
+        rc = opt_in_smem(ctx, zs_k_violations<true>, smem);
+        if (rc) return rc;
+        zs_k_violations<true><<<grid, kThreads, smem, st>>>(o, cam, ctx->frame.packed, poses, n, viol_out);
+    } else {
+        zs_k_violations<false><<<grid, kThreads, 0, st>>>(o, cam, ctx->frame.packed, poses, n, viol_out);
+    }
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
+extern "C" int zs_filter(zs_ctx* ctx, const int32_t* viol, int n, int n_pts, float inconst_ratio_th,
+                         int32_t* keep_idx_out, int32_t* n_keep_out, void* stream) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (n < 0 || n_pts <= 0 || !n_keep_out || (n > 0 && (!viol || !keep_idx_out)))
+        return zs_fail(ctx, ZS_ERR_INVALID, "zs_filter arguments");
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    zs_k_filter<<<1, 1024, 0, (cudaStream_t)stream>>>(viol, n, (float)n_pts, inconst_ratio_th, keep_idx_out, n_keep_out);
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
+static int project_common(zs_ctx* ctx, const float* poses, int n, const float* pts, int n_pts,
+                          float fx, float fy, float cx, float cy, int H, int W, int32_t* uv_out,
+                          const uint8_t* mask, int32_t* count_out, void* stream) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (n < 0 || n_pts <= 0 || !pts || !poses || ((uintptr_t)poses & 15))
+        return zs_fail(ctx, ZS_ERR_INVALID, "projection arguments");
+    if ((size_t)n_pts * 12 > kCloudSmemMax) return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "%d model points", n_pts);
+    if (n == 0) return ZS_OK;
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    zs_cam cam{fx, fy, cx, cy, 0.f, 0.f, H, W};
+    const size_t smem = (size_t)n_pts * 12;
+    const int grid = grid_for(ctx, n, 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (mask) {
+        rc = opt_in_smem(ctx, zs_k_project<true>, smem);
+        if (rc) return rc;
+        zs_k_project<true><<<grid, kThreads, smem, st>>>(poses, n, pts, n_pts, cam, nullptr, mask, count_out);
+    } else {
+        rc = opt_in_smem(ctx, zs_k_project<false>, smem);
+        if (rc) return rc;
+        zs_k_project<false><<<grid, kThreads, smem, st>>>(poses, n, pts, n_pts, cam, uv_out, nullptr, nullptr);
+    }
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
+extern "C" int zs_project_uv(zs_ctx* ctx, const float* poses, int n, const float* pts, int n_pts,
+                             float fx, float fy, float cx, float cy, int32_t* uv_out, void* stream) {
+    if (ctx && n > 0 && (!uv_out || ((uintptr_t)uv_out & 7))) return zs_fail(ctx, ZS_ERR_INVALID, "uv_out");
+    return project_common(ctx, poses, n, pts, n_pts, fx, fy, cx, cy, 0, 0, uv_out, nullptr, nullptr, stream);
+}
+
+extern "C" int zs_mask_count(zs_ctx* ctx, const float* poses, int n, const float* pts, int n_pts,
+                             float fx, float fy, float cx, float cy, const uint8_t* mask, int H, int W,
+                             int32_t* count_out, void* stream) {
+    if (ctx && (!mask || H <= 0 || W <= 0 || (n > 0 && !count_out))) return zs_fail(ctx, ZS_ERR_INVALID, "mask arguments");
+    return project_common(ctx, poses, n, pts, n_pts, fx, fy, cx, cy, H, W, nullptr, mask, count_out, stream);
+}

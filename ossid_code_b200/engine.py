@@ -1,0 +1,226 @@
+"""Torch-facing wrapper over the C ABI: one ``ZsContext`` per CUDA device.
+
+PyTorch is used for device memory and streams only; every computation is a call
+into libzs.so on ``torch.cuda.current_stream()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ZS_BF16, ZS_F32, check
+
+FEAT_DTYPES = {torch.float32: ZS_F32, torch.bfloat16: ZS_BF16}
+
+
+def _dev_f32(x, device) -> torch.Tensor:
+    """Single cast to float32 (on the host when the source is host memory), then to the device."""
+    t = torch.as_tensor(x)
+    if t.device.type == "cpu":
+        t = t.to(torch.float32).contiguous()
+        return t.to(device, non_blocking=True)
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def poses_to_rt12(transforms, device) -> torch.Tensor:
+    """(M,4,4) any float dtype -> (M,12) float32 rows of (R|t) on ``device`` (include/zs.h)."""
+    t = torch.as_tensor(transforms)
+    if t.ndim != 3 or t.shape[1:] != (4, 4):
+        raise ValueError(f"pose hypotheses must be (M,4,4), got {tuple(t.shape)}")
+    t = t[:, :3, :4].to(torch.float32).reshape(t.shape[0], 12).contiguous()
+    return t.to(device, non_blocking=True)
+
+
+class ZsContext:
+    """Owns a ``zs_ctx`` on one device."""
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise _lib.ZsError("CUDA device required: this path has no CPU fallback")
+        self.lib = _lib.load()
+        self.index = torch.device("cuda", device).index if not isinstance(device, int) else device
+        self.device = torch.device("cuda", self.index)
+        h = C.c_void_p()
+        rc = self.lib.zs_create(C.byref(h), self.index)
+        if rc != 0:
+            raise _lib.ZsError(f"zs_create(device={self.index}) failed: {self.lib.zs_strerror(rc).decode()}")
+        self.h = h
+        self.frame_hw = None
+        self.obj_npts = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.zs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ---------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ck(self, rc, what):
+        check(self.h, rc, what)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.zs_launch_count(self.h))
+
+    # -- uploads ----------------------------------------------------------------------
+    def set_frame(self, img01, depth, meta):
+        """img01 (H,W,3) in [0,1] (already blurred, /255), depth (H,W), meta = K2meta dict."""
+        rgb, dep = _dev_f32(img01, self.device), _dev_f32(depth, self.device)
+        H, W = dep.shape
+        if rgb.shape != (H, W, 3):
+            raise ValueError(f"img {tuple(rgb.shape)} does not match depth {tuple(dep.shape)}")
+        self._ck(self.lib.zs_set_frame(self.h, rgb.data_ptr(), dep.data_ptr(), H, W,
+                                       float(meta["camera_fx"]), float(meta["camera_fy"]),
+                                       float(meta["camera_cx"]), float(meta["camera_cy"]),
+                                       float(meta.get("camera_scale", 1.0)), self._stream()), "zs_set_frame")
+        self.frame_hw, self._keep = (H, W), (rgb, dep)
+
+    def set_frame_u8(self, img_u8, depth, meta, blur: bool = True):
+        """img_u8 (H,W,3) uint8 straight from the camera; blur + /255 + HSV run on the GPU."""
+        img = torch.as_tensor(img_u8)
+        if img.dtype != torch.uint8:
+            raise ValueError("img_u8 must be uint8")
+        img = img.contiguous().to(self.device, non_blocking=True)
+        dep = _dev_f32(depth, self.device)
+        H, W = dep.shape
+        if img.shape != (H, W, 3):
+            raise ValueError(f"img {tuple(img.shape)} does not match depth {tuple(dep.shape)}")
+        self._ck(self.lib.zs_set_frame_u8(self.h, img.data_ptr(), dep.data_ptr(), H, W,
+                                          float(meta["camera_fx"]), float(meta["camera_fy"]),
+                                          float(meta["camera_cx"]), float(meta["camera_cy"]),
+                                          float(meta.get("camera_scale", 1.0)), int(bool(blur)), self._stream()),
+                 "zs_set_frame_u8")
+        self.frame_hw, self._keep = (H, W), (img, dep)
+
+    def set_object(self, slot: int, points, colors, normals):
+        p, c, n = (_dev_f32(t, self.device) for t in (points, colors, normals))
+        if p.ndim != 2 or p.shape[1] != 3 or c.shape != p.shape or n.shape != p.shape:
+            raise ValueError("model_points/colors/normals must all be (N,3)")
+        self._ck(self.lib.zs_set_object(self.h, slot, p.data_ptr(), c.data_ptr(), n.data_ptr(), p.shape[0],
+                                        self._stream()), "zs_set_object")
+        self.obj_npts[slot] = p.shape[0]
+        self._keep_obj = (p, c, n)
+
+    def set_weights(self, slot: int, folded: dict):
+        from .weights import FOLDED_KEYS
+        blob = torch.cat([folded[k].detach().to(torch.float32).reshape(-1).cpu() for k in FOLDED_KEYS])
+        if blob.numel() != _lib.ZS_WEIGHT_FLOATS:
+            raise ValueError(f"folded weights have {blob.numel()} values, expected {_lib.ZS_WEIGHT_FLOATS}")
+        blob = blob.to(self.device)
+        self._ck(self.lib.zs_set_weights(self.h, slot, blob.data_ptr(), blob.numel(), self._stream()), "zs_set_weights")
+        torch.cuda.current_stream(self.device).synchronize()   # blob may be freed after return
+
+    # -- kernels ----------------------------------------------------------------------
+    def project_uv(self, poses12, points, meta) -> torch.Tensor:
+        pts = _dev_f32(points, self.device)
+        n = poses12.shape[0]
+        uv = torch.empty((n, pts.shape[0], 2), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.zs_project_uv(self.h, poses12.data_ptr(), n, pts.data_ptr(), pts.shape[0],
+                                        float(meta["camera_fx"]), float(meta["camera_fy"]),
+                                        float(meta["camera_cx"]), float(meta["camera_cy"]),
+                                        uv.data_ptr(), self._stream()), "zs_project_uv")
+        return uv
+
+    def mask_count(self, poses12, points, meta, mask) -> torch.Tensor:
+        pts = _dev_f32(points, self.device)
+        m = torch.as_tensor(mask)
+        m = (m != 0).to(torch.uint8).contiguous().to(self.device)
+        n = poses12.shape[0]
+        cnt = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.zs_mask_count(self.h, poses12.data_ptr(), n, pts.data_ptr(), pts.shape[0],
+                                        float(meta["camera_fx"]), float(meta["camera_fy"]),
+                                        float(meta["camera_cx"]), float(meta["camera_cy"]),
+                                        m.data_ptr(), m.shape[0], m.shape[1], cnt.data_ptr(), self._stream()),
+                 "zs_mask_count")
+        return cnt
+
+    def violations(self, slot: int, poses12) -> torch.Tensor:
+        n = poses12.shape[0]
+        viol = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.zs_violations(self.h, slot, poses12.data_ptr(), n, viol.data_ptr(), self._stream()),
+                 "zs_violations")
+        return viol
+
+    def filter(self, viol, n_pts: int, th: float) -> torch.Tensor:
+        """Kept hypothesis indices (ascending, int32).  Reads the count back: one 4-byte sync."""
+        n = viol.shape[0]
+        keep = torch.empty((max(n, 1),), dtype=torch.int32, device=self.device)
+        n_keep = torch.empty((1,), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.zs_filter(self.h, viol.data_ptr(), n, n_pts, float(th), keep.data_ptr(),
+                                    n_keep.data_ptr(), self._stream()), "zs_filter")
+        return keep[: int(n_keep.item())]
+
+    def features(self, slot: int, poses12, keep_idx: Optional[torch.Tensor] = None, n_keep: Optional[int] = None,
+                 dtype=torch.float32, want_uv: bool = False, want_mask: bool = False, want_viol: bool = False,
+                 out: Optional[torch.Tensor] = None):
+        N = self.obj_npts[slot]
+        if keep_idx is not None:
+            n_keep = keep_idx.shape[0]
+        elif n_keep is None:
+            n_keep = poses12.shape[0]
+        feat = out if out is not None else torch.empty((n_keep, N, 8), dtype=dtype, device=self.device)
+        uv = torch.empty((n_keep, N, 2), dtype=torch.int32, device=self.device) if want_uv else None
+        mask = torch.empty((n_keep, N), dtype=torch.uint8, device=self.device) if want_mask else None
+        viol = torch.empty((n_keep,), dtype=torch.int32, device=self.device) if want_viol else None
+        self._ck(self.lib.zs_features(self.h, slot, poses12.data_ptr(),
+                                      keep_idx.data_ptr() if keep_idx is not None else None, n_keep,
+                                      feat.data_ptr(), FEAT_DTYPES[feat.dtype],
+                                      uv.data_ptr() if want_uv else None, mask.data_ptr() if want_mask else None,
+                                      viol.data_ptr() if want_viol else None, self._stream()), "zs_features")
+        return feat, uv, mask, viol
+
+    def score(self, wslot: int, feat: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """feat (n,N,8) float32 -> fp32 CUDA-core path; bfloat16 -> tcgen05 path."""
+        if feat.ndim != 3 or feat.shape[2] != 8 or feat.dtype not in FEAT_DTYPES:
+            raise ValueError(f"point_x must be (n,N,8) float32/bfloat16, got {tuple(feat.shape)} {feat.dtype}")
+        feat = feat.contiguous()
+        n, N = feat.shape[0], feat.shape[1]
+        scores = out if out is not None else torch.empty((n,), dtype=torch.float32, device=self.device)
+        code = FEAT_DTYPES[feat.dtype]
+        self._ck(self.lib.zs_score(self.h, wslot, feat.data_ptr(), code, n, N, code, scores.data_ptr(),
+                                   self._stream()), "zs_score")
+        return scores
+
+    def pool(self, wslot: int, feat: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Shared per-point MLP + max over points: (n,N,8) -> (n,1024) float32."""
+        n, N = feat.shape[0], feat.shape[1]
+        pooled = out if out is not None else torch.empty((n, 1024), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.zs_pool(self.h, wslot, feat.data_ptr(), FEAT_DTYPES[feat.dtype], n, N, pooled.data_ptr(),
+                                  self._stream()), "zs_pool")
+        return pooled
+
+    def head(self, wslot: int, pooled: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n = pooled.shape[0]
+        scores = out if out is not None else torch.empty((n,), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.zs_head(self.h, wslot, pooled.data_ptr(), n, scores.data_ptr(), self._stream()), "zs_head")
+        return scores
+
+    def topk(self, scores: torch.Tensor, k: int, index_base: int = 0):
+        s = torch.empty((k,), dtype=torch.float32, device=self.device)
+        i = torch.empty((k,), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.zs_topk(self.h, scores.data_ptr(), scores.shape[0], k, index_base, s.data_ptr(),
+                                  i.data_ptr(), self._stream()), "zs_topk")
+        return s, i
+
+
+_contexts = {}
+
+
+def get_context(device=0) -> ZsContext:
+    idx = torch.device(device).index if not isinstance(device, int) else device
+    idx = 0 if idx is None else idx
+    if idx not in _contexts:
+        _contexts[idx] = ZsContext(idx)
+    return _contexts[idx]

@@ -1,0 +1,186 @@
+"""Multi-object, multi-GPU frame scoring on top of the C ABI.
+
+The reference scores one (object, frame) per ``networkInference`` call and takes
+``scores.argmax()`` (python/ossid/scripts/online_learning.py:464-468).  ``FrameScorer`` batches
+that over the objects of a frame, returns the per-object top-k by (score desc, hypothesis index
+asc) -- top-1 is exactly the reference's argmax -- and shards hypotheses across the ranks of a
+``torch.distributed`` group: each rank scores a contiguous slice of every object's hypothesis
+list, and the only data-path collective is one all-gather of k (score, index) records per object.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .engine import ZsContext, get_context, poses_to_rt12
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of ``n`` hypotheses owned by ``rank``; global index = lo + local index."""
+    per = -(-n // world) if n > 0 else 0
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k: int):
+    """Merge candidate lists (..., C) -> (..., k) by (score desc, index asc); empty slots are (-inf, -1).
+
+    Deterministic and identical on every rank, so top-1 does not depend on the GPU count.
+    """
+    s = torch.where(idx < 0, torch.full_like(scores, float("-inf")), scores)
+    s = torch.where(s != s, torch.full_like(s, float("-inf")), s)          # NaN never wins
+    big = torch.iinfo(idx.dtype).max
+    i_key = torch.where(idx < 0, torch.full_like(idx, big), idx)
+    o1 = torch.argsort(i_key, dim=-1, stable=True)
+    s1, i1 = torch.gather(s, -1, o1), torch.gather(idx, -1, o1)
+    o2 = torch.argsort(-s1, dim=-1, stable=True)
+    s2, i2 = torch.gather(s1, -1, o2), torch.gather(i1, -1, o2)
+    if s2.shape[-1] < k:
+        pad = k - s2.shape[-1]
+        s2 = torch.cat([s2, s2.new_full(s2.shape[:-1] + (pad,), float("-inf"))], -1)
+        i2 = torch.cat([i2, i2.new_full(i2.shape[:-1] + (pad,), -1)], -1)
+    return s2[..., :k].contiguous(), i2[..., :k].contiguous()
+
+
+def allgather_topk(s: torch.Tensor, i: torch.Tensor, k: int, group=None):
+    """(n_obj,k) local candidates on each rank -> merged (n_obj,k), same on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return merge_topk(s, i, k)
+    # one record per candidate: score bits and index side by side (indices ship as int32, not as floats)
+    rec = torch.stack([s.to(torch.float32).view(torch.int32), i.to(torch.int32)], dim=-1).contiguous()
+    parts = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(parts, rec, group=group)
+    out = torch.stack(parts)
+    gs = out[..., 0].view(torch.float32).permute(1, 0, 2).reshape(s.shape[0], -1)
+    gi = out[..., 1].permute(1, 0, 2).reshape(s.shape[0], -1)
+    return merge_topk(gs, gi.to(i.dtype), k)
+
+
+class FrameScorer:
+    """Scores all objects of one RGB-D frame and returns per-object top-k hypotheses.
+
+    ``weights``: list of folded weight dicts (``weights.fold_state_dict``); ``weight_of(obj_index)``
+    picks one per object (the reference keys two YCB-V scorers on object-id parity,
+    online_learning.py:461-463).
+    """
+
+    def __init__(self, weights: Sequence[dict], device: Optional[int] = None, precision: str = "bf16",
+                 inconst_ratio_th: float = 100.0, k: int = 8, chunk: int = 32768, group=None,
+                 ctx: Optional[ZsContext] = None):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.ctx = ctx or get_context(device)
+        self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.th, self.k, self.chunk, self.group = float(inconst_ratio_th), int(k), int(chunk), group
+        for slot, w in enumerate(weights):
+            self.ctx.set_weights(slot, w)
+        self.n_weights = len(weights)
+        self._feat = None
+        self._pooled = None
+        self._resident = None
+        self.stage_events = None     # set to [] to record (stage, units, start_event, end_event) per launch group
+
+    def _mark(self, stage, units, prev=None):
+        """Stage timing hook: closes the previous stage's CUDA-event pair and opens the next one."""
+        if self.stage_events is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.ctx.device))
+        if prev is not None:
+            self.stage_events.append((prev[0], prev[1], prev[2], ev))
+        return (stage, units, ev) if stage is not None else None
+
+    def stage_times_ms(self):
+        """Sum of event-timed milliseconds, launch-group count and units per stage (after a synchronize)."""
+        out = {}
+        for stage, units, a, b in self.stage_events or []:
+            t = out.setdefault(stage, dict(ms=0.0, calls=0, units=0))
+            t["ms"] += a.elapsed_time(b)
+            t["calls"] += 1
+            t["units"] += units
+        return out
+
+    # -- distributed plumbing ---------------------------------------------------------
+    def _rank_world(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(self.group), dist.get_world_size(self.group)
+        return 0, 1
+
+    # -- upload (host -> HBM) ---------------------------------------------------------
+    def upload(self, img_u8, depth, cam_K, objects: List[dict], weight_of=lambda o: 0):
+        """Copy one frame's inputs to the device and keep them resident; this rank's pose slices only."""
+        from .zephyr_utils import K2meta
+        ctx = self.ctx
+        rank, world = self._rank_world()
+        meta = {k: float(v) for k, v in K2meta(np.asarray(cam_K)).items()}
+        ctx.set_frame_u8(img_u8, depth, meta, blur=True)
+        res = []
+        for o, ob in enumerate(objects):
+            slot = o % 64
+            ctx.set_object(slot, ob["model_points"], ob["model_colors"], ob["model_normals"])
+            M = len(ob["pose_hypos"])
+            lo, hi = shard_range(M, rank, world)
+            poses12 = poses_to_rt12(torch.as_tensor(ob["pose_hypos"])[lo:hi], ctx.device)
+            res.append(dict(slot=slot, poses12=poses12, lo=lo, M=M, wslot=weight_of(o) % max(self.n_weights, 1)))
+        self._resident = res
+        return res
+
+    # -- compute (everything resident) --------------------------------------------------
+    def run_resident(self):
+        """Featurise + score + top-k for the uploaded frame.  Returns (scores (n_obj,k), index (n_obj,k))
+        tensors on the device; indices are global hypothesis indices per object, -1 = empty slot."""
+        ctx, k = self.ctx, self.k
+        top_s, top_i = [], []
+        for r in self._resident:
+            poses12, N = r["poses12"], ctx.obj_npts[r["slot"]]
+            m = poses12.shape[0]
+            keep = None
+            if self.th < 100 and m > 0:
+                keep = ctx.filter(ctx.violations(r["slot"], poses12), N, self.th)
+            n_keep = m if keep is None else keep.shape[0]
+            scores = torch.empty((n_keep,), dtype=torch.float32, device=ctx.device)
+            for s in range(0, n_keep, self.chunk):
+                e = min(s + self.chunk, n_keep)
+                need = (e - s) * N * 8
+                if self._feat is None or self._feat.numel() < need or self._feat.dtype != self.dtype:
+                    self._feat = torch.empty((max(need, min(self.chunk, max(n_keep, 1)) * N * 8),),
+                                             dtype=self.dtype, device=ctx.device)
+                feat = self._feat[:need].view(e - s, N, 8)
+                if self._pooled is None or self._pooled.shape[0] < e - s:
+                    self._pooled = torch.empty((max(e - s, min(self.chunk, n_keep)), 1024), dtype=torch.float32,
+                                               device=ctx.device)
+                t = self._mark("features", (e - s) * N)
+                if keep is None:
+                    ctx.features(r["slot"], poses12[s:e], n_keep=e - s, out=feat)
+                else:
+                    ctx.features(r["slot"], poses12, keep_idx=keep[s:e], out=feat)
+                t = self._mark("pool", (e - s) * N, t)
+                pooled = ctx.pool(r["wslot"], feat, out=self._pooled[: e - s])
+                t = self._mark("head", e - s, t)
+                ctx.head(r["wslot"], pooled, out=scores[s:e])
+                self._mark(None, 0, t)
+            ts, ti = ctx.topk(scores, k, 0)
+            if keep is not None and n_keep > 0:      # position in the kept list -> local hypothesis index
+                ti = torch.where(ti >= 0, keep[ti.clamp(min=0).long()], ti)
+            ti = torch.where(ti >= 0, ti + r["lo"], ti)
+            top_s.append(ts)
+            top_i.append(ti)
+        S, I = torch.stack(top_s), torch.stack(top_i)
+        rank, world = self._rank_world()
+        if world > 1:
+            S, I = allgather_topk(S, I, k, self.group)
+        return S, I
+
+    # -- public end-to-end call -------------------------------------------------------------
+    def score_frame(self, img_u8, depth, cam_K, objects: List[dict], weight_of=lambda o: 0):
+        """Host buffers in, host results out: ``(scores (n_obj,k), indices (n_obj,k))`` numpy arrays."""
+        self.upload(img_u8, depth, cam_K, objects, weight_of)
+        S, I = self.run_resident()
+        return S.cpu().numpy(), I.cpu().numpy()

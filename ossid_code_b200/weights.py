@@ -42,6 +42,7 @@ def seeded_state_dict(seed: int = 0, dim_point: int = DIM_POINT, num_class: int 
             sd[f"{bn}.bias"] = 0.05 * torch.randn(co, generator=g)
             sd[f"{bn}.running_mean"] = 0.1 * torch.randn(co, generator=g)
             sd[f"{bn}.running_var"] = 1.0 + 0.2 * torch.rand(co, generator=g)
+            sd[f"{bn}.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
     return sd
 
 

@@ -1,0 +1,286 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run on the B200: pytest -m gpu.
+
+Bars (BASELINE.json north_star): pixel indices, masks, violation counts, kept sets: bit-exact;
+features and fp32 scores: 1e-4 relative; bf16 tensor-core scores: 1e-2; identical top-1.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import zephyr_oracle as zo
+from ossid_code_b200 import scoring, synthetic as syn, weights, zephyr_shim, zephyr_utils as glue
+from ossid_code_b200.engine import get_context, poses_to_rt12
+
+pytestmark = pytest.mark.gpu
+
+FEAT_RTOL, FEAT_ATOL = 1e-4, 1e-6          # fp32 features
+BF16_FEAT_RTOL = 2 ** -8                   # one bf16 rounding of an fp32 feature
+SCORE_F32_RTOL = 1e-4                      # of the score vector's max magnitude
+SCORE_BF16_RTOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return get_context(0)
+
+
+def _scene(seed, intr="tiny", n_pts=200, n_hypo=64, n_obj=1):
+    sc = syn.make_scene(seed, intr, n_obj=n_obj, n_pts=n_pts, n_hypo=n_hypo)
+    import cv2
+    sc["img01"] = cv2.GaussianBlur(sc["img"], (5, 5), 0) / 255.
+    sc["meta"] = glue.K2meta(sc["cam_K"])
+    return sc
+
+
+def _oracle_features(sc, ob, poses=None):
+    return zo.features(sc["img01"], sc["depth"], ob["pose_hypos"] if poses is None else poses, sc["meta"],
+                       ob["model_points"], ob["model_colors"], ob["model_normals"])
+
+
+def _gpu_features(ctx, sc, ob, dtype=torch.float32, poses=None, keep=None):
+    ctx.set_frame(sc["img01"], sc["depth"], sc["meta"])
+    ctx.set_object(0, ob["model_points"], ob["model_colors"], ob["model_normals"])
+    p12 = poses_to_rt12(ob["pose_hypos"] if poses is None else poses, ctx.device)
+    return ctx.features(0, p12, keep_idx=keep, dtype=dtype, want_uv=True, want_mask=True, want_viol=True)
+
+
+def _assert_feat_close(got, ref, rtol=FEAT_RTOL, atol=FEAT_ATOL):
+    got, ref = got.float().cpu(), ref
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bool(bad.any()), f"{int(bad.sum())} features off; worst abs err {float(err.max()):.3e}"
+
+
+@pytest.mark.parametrize("seed,intr,n_pts,n_hypo", [(1, "tiny", 200, 64), (2, "lmo", 1000, 300), (3, "ycbv", 333, 97),
+                                                   (4, "hd", 1000, 120), (5, "tiny", 1, 5), (6, "tiny", 31, 33),
+                                                   (7, "tiny", 33, 1)])
+def test_features_fp32_bit_exact_integers_and_close_floats(ctx, seed, intr, n_pts, n_hypo):
+    sc = _scene(seed, intr, n_pts, n_hypo)
+    ob = sc["objects"][0]
+    ref = _oracle_features(sc, ob)
+    feat, uv, mask, viol = _gpu_features(ctx, sc, ob)
+    assert torch.equal(uv.cpu(), ref["uv"]), "pixel indices differ"
+    assert torch.equal(mask.cpu(), ref["mask"]), "visibility masks differ"
+    assert torch.equal(viol.cpu(), ref["viol"]), "free-space violation counts differ"
+    _assert_feat_close(feat, ref["point_x"])
+    if n_hypo >= 60:                                       # the scene really exercises every mask bit
+        for bit in (zo.BIT_VALID_PROJ, zo.BIT_VALID_DEPTH, zo.BIT_FRONT, zo.BIT_FREE_SPACE, zo.BIT_OCCLUDED):
+            assert int((ref["mask"] & bit).ne(0).sum()) > 0
+
+
+def test_features_bf16_is_rounded_fp32(ctx):
+    sc = _scene(11, "lmo", 500, 128)
+    ob = sc["objects"][0]
+    ref = _oracle_features(sc, ob)
+    feat, uv, mask, _ = _gpu_features(ctx, sc, ob, dtype=torch.bfloat16)
+    assert torch.equal(uv.cpu(), ref["uv"]) and torch.equal(mask.cpu(), ref["mask"])
+    f32, _, _, _ = _gpu_features(ctx, sc, ob, dtype=torch.float32)
+    assert torch.equal(feat, f32.to(torch.bfloat16)), "bf16 features are not RNE(fp32 features)"
+    _assert_feat_close(feat, ref["point_x"], rtol=BF16_FEAT_RTOL, atol=1e-6)
+
+
+def test_degenerate_hypotheses(ctx):
+    """Identity placeholders (online_learning.py:431), z<=0, NaN/inf poses, far off-frame: all defined, all equal."""
+    sc = _scene(12, "tiny", 100, 8)
+    ob = sc["objects"][0]
+    P = np.repeat(np.eye(4)[None], 8, axis=0)
+    P[1, 2, 3] = -0.5
+    P[2, 2, 3] = 0.0
+    P[3, 0, 3] = np.nan
+    P[4, 2, 3] = np.inf
+    P[5, :3, 3] = [1e30, 0, 1.0]
+    P[6] = ob["gt_pose"]
+    P[7] = ob["gt_pose"]; P[7, :3, :3] *= 1e-30
+    ref = _oracle_features(sc, ob, poses=P)
+    feat, uv, mask, viol = _gpu_features(ctx, sc, ob, poses=P)
+    assert torch.equal(uv.cpu(), ref["uv"]) and torch.equal(mask.cpu(), ref["mask"]) and torch.equal(viol.cpu(), ref["viol"])
+    assert torch.isfinite(feat).all()
+    _assert_feat_close(feat, ref["point_x"])
+    assert int((mask[6] & 1).sum()) > 0 and int((mask[1] & 1).sum()) == 0
+
+
+def test_empty_hypothesis_list(ctx):
+    sc = _scene(13, "tiny", 50, 4)
+    ob = sc["objects"][0]
+    feat, uv, mask, viol = _gpu_features(ctx, sc, ob, poses=np.zeros((0, 4, 4)))
+    assert feat.shape == (0, 50, 8) and uv.shape == (0, 50, 2)
+    s, i = ctx.topk(torch.zeros(0, device=ctx.device), 3)
+    assert i.tolist() == [-1, -1, -1] and all(v == float("-inf") for v in s.tolist())
+    assert ctx.filter(torch.zeros(0, dtype=torch.int32, device=ctx.device), 50, 10.0).numel() == 0
+
+
+@pytest.mark.parametrize("th", [10.0, 3.0, 0.5, 100.0])
+def test_violation_prefilter_and_compaction(ctx, th):
+    sc = _scene(14, "lmo", 400, 2500)
+    ob = sc["objects"][0]
+    ref = _oracle_features(sc, ob)
+    ctx.set_frame(sc["img01"], sc["depth"], sc["meta"])
+    ctx.set_object(0, ob["model_points"], ob["model_colors"], ob["model_normals"])
+    p12 = poses_to_rt12(ob["pose_hypos"], ctx.device)
+    viol = ctx.violations(0, p12)
+    assert torch.equal(viol.cpu(), ref["viol"])
+    keep = ctx.filter(viol, 400, th)
+    exp = zo.violation_filter(ref["viol"], 400, th)
+    assert keep.cpu().tolist() == exp.tolist()
+    feat, uv, mask, _ = ctx.features(0, p12, keep_idx=keep, want_uv=True, want_mask=True)
+    assert torch.equal(uv.cpu(), ref["uv"][exp]) and torch.equal(mask.cpu(), ref["mask"][exp])
+    _assert_feat_close(feat, ref["point_x"][exp])
+
+
+def test_filter_never_empty(ctx):
+    viol = torch.tensor([70, 60, 60, 90], dtype=torch.int32, device=ctx.device)
+    assert ctx.filter(viol, 100, 10.0).tolist() == [1]
+
+
+def test_project_uv_and_mask_filter_match_golden(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "mask_filter.npz"))
+    meta = glue.K2meta(g["cam_K"])
+    uv = zephyr_shim.projectPointsUv(g["pose_hypos"], g["model_points"], meta)
+    assert uv.dtype == np.int64 and np.array_equal(uv, zo.project_raw(g["pose_hypos"], g["model_points"], meta).numpy())
+    for th, key in ((0.5, "kept_050"), (0.9, "kept_090"), (0.0, "kept_000")):
+        kept = glue.filterHypoByMask(g["model_points"], meta, g["pose_hypos"], g["mask"], th=th)
+        assert np.array_equal(kept, g[key]), f"filterHypoByMask th={th}"
+
+
+def test_projection_matches_reference_fixture(ctx, golden_dir):
+    """GPU uv / front-facing selection vs the reference's projectModelPoint output (fixture)."""
+    g = np.load(os.path.join(golden_dir, "projection.npz"))
+    H, W = int(g["H"]), int(g["W"])
+    meta = dict(camera_fx=float(g["fx"]), camera_fy=float(g["fy"]), camera_cx=float(g["cx"]), camera_cy=float(g["cy"]), camera_scale=1.0)
+    ctx.set_frame(np.zeros((H, W, 3)), np.ones((H, W)), meta)
+    ctx.set_object(0, g["model_points"], np.zeros_like(g["model_points"]), g["model_normals"])
+    feat, uv, mask, _ = ctx.features(0, poses_to_rt12(g["poses"], ctx.device), want_uv=True, want_mask=True)
+    uv, mask, offs = uv.cpu().numpy(), mask.cpu().numpy(), g["ref_offsets"]
+    for i in range(len(g["poses"])):
+        sel = ((mask[i] & 1) != 0) & ((mask[i] & 4) != 0)
+        assert np.array_equal(np.nonzero(sel)[0], g["ref_idx"][offs[i]:offs[i + 1]])
+        assert np.array_equal(uv[i][sel], g["ref_uv"][offs[i]:offs[i + 1]])
+    valid = (mask & 1) != 0
+    np.testing.assert_allclose(feat[..., 6].cpu().numpy()[valid], g["ref_cos"].T[valid], atol=1e-5, rtol=0)
+
+
+def test_gpu_blur_frontend_is_bit_identical_to_cv2_path(ctx):
+    sc = _scene(15, "lmo", 300, 64)
+    ob = sc["objects"][0]
+    f_host, uv_h, mk_h, _ = _gpu_features(ctx, sc, ob)
+    ctx.set_frame_u8(sc["img"], sc["depth"], sc["meta"], blur=True)
+    p12 = poses_to_rt12(ob["pose_hypos"], ctx.device)
+    f_gpu, uv_g, mk_g, _ = ctx.features(0, p12, want_uv=True, want_mask=True)
+    assert torch.equal(f_host, f_gpu) and torch.equal(uv_h, uv_g) and torch.equal(mk_h, mk_g)
+
+
+def _score_tol(ref, rtol):
+    return rtol * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("n,N", [(1, 1), (3, 127), (5, 128), (4, 129), (40, 1000), (2, 4000)])
+def test_scorer_fp32_matches_oracle(ctx, n, N):
+    g = torch.Generator().manual_seed(n * 1000 + N)
+    x = torch.randn(n, N, 8, generator=g) * 0.5
+    w = weights.seeded_folded(1)
+    ctx.set_weights(0, w)
+    got = ctx.score(0, x.to(ctx.device)).cpu()
+    ref = zo.scorer(x, w)
+    assert float((got - ref).abs().max()) <= _score_tol(ref, SCORE_F32_RTOL) + 1e-6
+
+
+def test_topk_matches_oracle_with_ties(ctx):
+    g = torch.Generator().manual_seed(5)
+    s = torch.randn(5000, generator=g)
+    s[17] = s[4000] = s[123] = float(s.max()) + 1.0
+    s[99] = float("nan")
+    ts, ti = ctx.topk(s.to(ctx.device), 16, index_base=1000)
+    clean = torch.where(s != s, torch.full_like(s, float("-inf")), s)
+    es, ei = zo.topk(clean, 16, index_base=1000)
+    assert ti.cpu().tolist() == ei.tolist() and ti[0].item() == 1017
+    assert int(np.argmax(clean.numpy())) + 1000 == ti[0].item()
+    ts, ti = ctx.topk(s[:3].to(ctx.device), 8)
+    assert ti.cpu().tolist()[3:] == [-1] * 5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag,th", [("th100", 100.0), ("th10", 10.0)])
+def test_networkInference_drop_in_matches_reference_fixture(golden_dir, precision, tag, th):
+    """The reference's scoring API, end to end on the GPU, vs what the reference's own
+    networkInference returned (fixture) for the same inputs."""
+    g = np.load(os.path.join(golden_dir, "network_inference.npz"))
+    zephyr_shim.install()
+    from zephyr.datasets.score_dataset import ScoreDataset
+    from zephyr.models.pointnet2 import PointNet2SSG
+    args = type("Args", (), dict(inconst_ratio_th=th, zs_precision=precision))()
+    ds = ScoreDataset([], "", "lmo", args, mode="test")
+    model = PointNet2SSG(ds.dim_point, args, num_class=1)
+    model.load_state_dict(weights.seeded_state_dict(int(g["weight_seed"])))
+    model = model.to(0).eval()
+    data = dict(img=g["img"], depth=g["depth"], cam_K=g["cam_K"], model_colors=g["model_colors"],
+                model_points=g["model_points"], model_normals=g["model_normals"],
+                pose_hypos=g["pose_hypos"].copy(), pp_err=np.arange(len(g["pose_hypos"]), dtype=np.float64))
+    poses, scores, errs, uv, dt = glue.networkInference(model, ds, data, return_time=True)
+    ref_scores = g[f"{tag}_scores"]
+    assert np.array_equal(poses, g[f"{tag}_poses"]), "kept pose set differs"
+    assert np.array_equal(np.asarray(errs), g[f"{tag}_pp_err"])
+    assert np.array_equal(glue.to_np(uv), g[f"{tag}_uv"].astype(np.int64)), "uv_original differs"
+    scores = np.asarray(scores).reshape(-1)
+    rtol = SCORE_F32_RTOL if precision == "fp32" else SCORE_BF16_RTOL
+    assert np.abs(scores - ref_scores).max() <= rtol * np.abs(ref_scores).max() + 1e-6
+    order = np.sort(ref_scores)[::-1]
+    if order[0] - order[1] > 2 * rtol * np.abs(ref_scores).max():
+        assert int(scores.argmax()) == int(ref_scores.argmax()), "top-1 hypothesis differs"
+
+
+def test_frame_scorer_top1_matches_oracle_fp32(ctx):
+    sc = _scene(21, "lmo", 256, 400, n_obj=3)
+    w = weights.seeded_folded(0)
+    fs = scoring.FrameScorer([w], device=0, precision="fp32", inconst_ratio_th=10.0, k=4, chunk=150)
+    S, I = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"])
+    for o, ob in enumerate(sc["objects"]):
+        f = _oracle_features(sc, ob)
+        keep = zo.violation_filter(f["viol"], 256, 10.0)
+        ref = zo.scorer(f["point_x"][keep], w)
+        es, ei = zo.topk(ref, 4)
+        exp_idx = keep[ei].tolist()
+        margin = float(es[0] - es[1]) if len(es) > 1 else 1.0
+        if margin > 2 * SCORE_F32_RTOL * float(ref.abs().max()):
+            assert int(I[o, 0]) == exp_idx[0], f"object {o}: top-1 differs"
+        np.testing.assert_allclose(S[o, :len(es)], es.numpy(), rtol=0, atol=_score_tol(ref, SCORE_F32_RTOL) + 1e-6)
+
+
+# --- full-size, size-independent properties (BASELINE.json configs[1] shape) -------------------------
+def test_full_size_properties(ctx):
+    """10k hypotheses x 1000 points: permutation equivariance, duplicate consistency, chunk invariance."""
+    sc = syn.make_scene(31, "ycbv", n_obj=1, n_pts=1000, n_hypo=10000)
+    ob = sc["objects"][0]
+    meta = glue.K2meta(sc["cam_K"])
+    ctx.set_frame_u8(sc["img"], sc["depth"], meta)
+    ctx.set_object(0, ob["model_points"], ob["model_colors"], ob["model_normals"])
+    w = weights.seeded_folded(0)
+    ctx.set_weights(0, w)
+    P = ob["pose_hypos"]
+    p12 = poses_to_rt12(P, ctx.device)
+    feat, uv, mask, viol = ctx.features(0, p12, want_uv=True, want_mask=True, want_viol=True)
+    perm = torch.randperm(len(P), generator=torch.Generator().manual_seed(0))
+    featp, uvp, maskp, violp = ctx.features(0, p12[perm.to(ctx.device)].contiguous(), want_uv=True, want_mask=True, want_viol=True)
+    assert torch.equal(featp, feat[perm.to(ctx.device)]) and torch.equal(uvp, uv[perm.to(ctx.device)])
+    assert torch.equal(maskp, mask[perm.to(ctx.device)]) and torch.equal(violp, viol[perm.to(ctx.device)])
+    assert torch.equal(viol, (mask & 8).ne(0).sum(1).to(torch.int32))          # counts are the mask's popcount
+    assert torch.equal(viol, ctx.violations(0, p12))
+    H, W = sc["H"], sc["W"]
+    vp = (mask & 1).ne(0)
+    assert bool(((uv[..., 0] >= 0) & (uv[..., 0] < W) & (uv[..., 1] >= 0) & (uv[..., 1] < H)).all())
+    assert bool((uv[~vp] == 0).all()) and bool((feat[~vp] == 0).all())
+    scores = ctx.score(0, feat)
+    scores_p = ctx.score(0, featp)
+    assert torch.equal(scores_p, scores[perm.to(ctx.device)]), "scores depend on batch position"
+    # oracle spot check on a slice
+    sl = slice(4000, 4064)
+    import cv2
+    img01 = cv2.GaussianBlur(sc["img"], (5, 5), 0) / 255.
+    ref = zo.features(img01, sc["depth"], P[sl], meta, ob["model_points"], ob["model_colors"], ob["model_normals"])
+    assert torch.equal(uv[sl].cpu(), ref["uv"]) and torch.equal(mask[sl].cpu(), ref["mask"])
+    rs = zo.scorer(ref["point_x"], w)
+    assert float((scores[sl].cpu() - rs).abs().max()) <= _score_tol(rs, SCORE_F32_RTOL) + 1e-6
+    ts, ti = ctx.topk(scores, 8)
+    assert int(ti[0]) == int(torch.argmax(scores))
