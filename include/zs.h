@@ -140,6 +140,12 @@ ZS_API int zs_pool(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtyp
             float* pooled_out, void* stream);
 ZS_API int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n, float* scores_out, void* stream);
 
+/* Diagnostic twin of zs_pool for bf16 features: additionally dumps the bf16-rounded activations
+ * of layers 1 and 2 (h1_out [dev] float32 [n*n_pts][64], h2_out [dev] float32 [n*n_pts][128];
+ * either may be NULL).  Used by the parity tests to localise a tensor-core mismatch. */
+ZS_API int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat_bf16, int n, int n_pts, float* pooled_out,
+                  float* h1_out, float* h2_out, void* stream);
+
 /* Per-object top-k, ordered by (score desc, index asc); k <= ZS_MAX_TOPK.  Generalises
  * `scores.argmax()` (online_learning.py:466-467; first maximum wins ties).
  * s_out [dev] float32 [k], i_out [dev] int32 [k] (= local index + index_base); entries

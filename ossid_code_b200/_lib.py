@@ -33,6 +33,7 @@ SIGNATURES = {
     "zs_score": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p]),
     "zs_pool": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "zs_head": (_i, [_p, _i, _p, _i, _p, _p]),
+    "zs_pool_debug": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p]),
     "zs_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
 }
 

@@ -119,9 +119,8 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
                     f5 = dD;
                     // cos of the angle between the viewing ray and the rotated normal
                     // (python/ossid/datasets/ycbv_object.py:74); 1e-4 feature, so rsqrt is fine
-                    const float q = (x * x + y * y + z * z) * (nx * nx + ny * ny + nz * nz);
-                    const float c = dot * rsqrtf(q);
-                    f6 = (c == c) ? c : 0.f;
+                    const float c = dot * rsqrtf(x * x + y * y + z * z) * rsqrtf(nx * nx + ny * ny + nz * nz);
+                    f6 = (fabsf(c) <= 3.402823466e38f) ? c : 0.f;      // NaN / inf (degenerate pose) -> 0
                 }
             }
             viol += __popc(__ballot_sync(0xffffffffu, (mk & ZS_BIT_FREE_SPACE) != 0));

@@ -1,7 +1,430 @@
-// placeholder until the tcgen05 kernel lands
+// Kernel 2: shared per-point MLP 8 -> 64 -> 128 -> 1024 + max over points on the 5th-generation
+// tensor cores (tcgen05.mma, bf16 operands, fp32 accumulators in TMEM), sm_100a only.
+// Reference call: model({"point_x": ...}), python/ossid/utils/zephyr_utils.py:34.
+//
+// Work split.  Persistent kernel, one CTA per SM.  CTAs come in pairs (2j, 2j+1) that walk the same
+// hypotheses; CTA `half` owns output channels [512*half, 512*half+512) of layer 3, whose bf16
+// weights (128 KB) stay resident in its shared memory for the whole launch.  Layers 1-2 (6 % of
+// the MACs) are recomputed by both CTAs of a pair, which keeps the two CTAs independent: no
+// cluster, no DSMEM, no cross-CTA reduction (the halves write disjoint channels of pooled[]).
+//
+// Tile = 128 consecutive points of one hypothesis.
+//   L1  D1[128 pts x  64] = X [128 x 16(8 real + 8 zero)] . W1^T      M=128 N=64  K=16  (1 MMA)
+//   L2  D2[128 pts x 128] = H1[128 x 64]  . W2^T                      M=128 N=128 K=64  (4 MMAs)
+//   L3  D3[128 ch  x 128 pts] = W3blk[128 x 128] . H2^T, 4 channel blocks  M=128 N=128 K=128 (8 MMAs each)
+// L1/L2 put points on TMEM lanes, so the epilogue thread of a point holds its whole channel row and
+// writes it as the next layer's K-major, 128B-swizzled operand with 16-byte stores.  L3 puts
+// CHANNELS on lanes and points on columns, so max-over-points is a register-only reduction in the
+// thread that owns the channel; bias + ReLU commute with max and are applied once per hypothesis.
+//
+// Warp roles (320 threads): warps 0-3 front epilogues (D1 -> H1, D2 -> H2), warps 4-7 max-pool
+// epilogue (D3), warp 8 bulk-copy producer (weights once, then feature tiles, 3 stages), warp 9
+// TMEM allocator + single-thread MMA issuer.  Front of tile i+1 overlaps layer 3 of tile i; D3 is
+// double-buffered in TMEM (cols: D1 0-63, D2 64-191, D3 192-319 / 320-447).  H1 aliases the H2
+// buffer that the same tile's epilogue 2 overwrites afterwards, which is what makes two H2
+// buffers + the resident weights fit in 227 KB.
+#include <cuda.h>
+
 #include "zs_common.cuh"
-int zs_tc_prepare_weights(zs_ctx*, int, cudaStream_t) { return ZS_OK; }
+
+namespace {
+
+constexpr int kTile = 128;               // points per tile
+constexpr int kThreadsTc = 320;
+constexpr int kStages = 3;
+
+// ---- shared-memory map (bytes from a 1024-aligned base) ---------------------------------------
+constexpr uint32_t kSmW3 = 0;                          // 4 blocks x 2 k-halves x 16 KB
+constexpr uint32_t kSmW2 = kSmW3 + 131072;             // 16 KB
+constexpr uint32_t kSmA3 = kSmW2 + 16384;              // 2 x 32 KB  (H2; first 16 KB doubles as H1)
+constexpr uint32_t kSmW1 = kSmA3 + 2 * 32768;          // 2 KB
+constexpr uint32_t kSmX = kSmW1 + 2048;                // 3 x 2 KB feature tiles
+constexpr uint32_t kSmZero = kSmX + kStages * 2048;    // 2 KB of zeros (upper K half of X)
+constexpr uint32_t kSmB1 = kSmZero + 2048;             // 64 floats
+constexpr uint32_t kSmB2 = kSmB1 + 256;                // 128 floats
+constexpr uint32_t kSmBar = kSmB2 + 512;               // mbarriers
+constexpr uint32_t kSmTmemPtr = kSmBar + 256;
+constexpr uint32_t kSmBytes = kSmTmemPtr + 16;
+constexpr uint32_t kSmAlloc = kSmBytes + 1024;         // slack for manual 1024-B alignment
+static_assert(kSmAlloc <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+// barrier slots
+enum : int {
+    BAR_W_FULL = 0, BAR_X_FULL = 1 /*3*/, BAR_X_EMPTY = 4 /*3*/, BAR_D1_FULL = 7, BAR_A2_FULL = 8, BAR_D2_FULL = 9,
+    BAR_A3_FULL = 10 /*2*/, BAR_A3_EMPTY = 12 /*2*/, BAR_D3_FULL = 14 /*2*/, BAR_D3_EMPTY = 16 /*2*/, BAR_COUNT = 18
+};
+
+// TMEM columns
+constexpr uint32_t kColD1 = 0, kColD2 = 64, kColD3 = 192;
+constexpr uint32_t kTmemCols = 512;
+
+// global image of the bf16 operands (bytes): W3 half 0, W3 half 1, W2, W1
+constexpr size_t kImgW3Half = 131072, kImgW2 = 2 * kImgW3Half, kImgW1 = kImgW2 + 16384, kImgBytes = kImgW1 + 2048;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2;
+
+// Instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// byte offset of 16-byte chunk `c` (8 bf16) of row `r` in a [rows x 64 bf16] 128B-swizzled K-major tile
+__host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c) { return r * 128u + (((c ^ (r & 7u)) & 7u) << 4); }
+
+// ---- the kernel ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsTc, 1)
+zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t* __restrict__ wimg,
+            const float* __restrict__ wf32, float* __restrict__ pooled, float* __restrict__ dbg_h1,
+            float* __restrict__ dbg_h2) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
+    auto bar = [&](int i) { return sbase + kSmBar + 8u * (uint32_t)i; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = blockIdx.x & 1, pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int T = (N + kTile - 1) / kTile;
+    const int n_loc = pair < n ? (n - pair + n_pairs - 1) / n_pairs : 0;
+    const int total = n_loc * T;
+    const long long total_rows = (long long)n * N;
+
+    // ---- one-time setup ------------------------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(bar(BAR_W_FULL), 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_X_FULL + s), 1); mbar_init(bar(BAR_X_EMPTY + s), 1); }
+        mbar_init(bar(BAR_D1_FULL), 1); mbar_init(bar(BAR_A2_FULL), 1); mbar_init(bar(BAR_D2_FULL), 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar(BAR_A3_FULL + b), 1); mbar_init(bar(BAR_A3_EMPTY + b), 1);
+            mbar_init(bar(BAR_D3_FULL + b), 1); mbar_init(bar(BAR_D3_EMPTY + b), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // zero the feature stages and the zero block (stale bytes must be finite), stage the small biases
+    for (int i = tid; i < (int)((kStages + 1) * 2048 / 16); i += kThreadsTc)
+        reinterpret_cast<uint4*>(sm + kSmX)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 64; i += kThreadsTc) reinterpret_cast<float*>(sm + kSmB1)[i] = wf32[ZS_OFF_B1 + i];
+    for (int i = tid; i < 128; i += kThreadsTc) reinterpret_cast<float*>(sm + kSmB2)[i] = wf32[ZS_OFF_B2 + i];
+    fence_proxy_async();
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmTmemPtr), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kSmTmemPtr);
+
+    if (warp == 8) {
+        // ===== bulk-copy producer =================================================================
+        if (lane == 0) {
+            mbar_expect_tx(bar(BAR_W_FULL), 131072 + 16384 + 2048);
+            for (int c = 0; c < 8; ++c)
+                bulk_g2s(sbase + kSmW3 + c * 16384, wimg + (size_t)half * kImgW3Half + (size_t)c * 16384, 16384, bar(BAR_W_FULL));
+            bulk_g2s(sbase + kSmW2, wimg + kImgW2, 16384, bar(BAR_W_FULL));
+            bulk_g2s(sbase + kSmW1, wimg + kImgW1, 2048, bar(BAR_W_FULL));
+            for (int i = 0; i < total; ++i) {
+                const int s = i % kStages, j = i / T, tt = i - j * T;
+                const long long row0 = (long long)(pair + j * n_pairs) * N + (long long)tt * kTile;
+                const long long left = (total_rows - row0) * 16;
+                const uint32_t bytes = left < 2048 ? (uint32_t)left : 2048u;
+                mbar_wait(bar(BAR_X_EMPTY + s), ((i / kStages) & 1) ^ 1);
+                mbar_expect_tx(bar(BAR_X_FULL + s), bytes);
+                bulk_g2s(sbase + kSmX + s * 2048, reinterpret_cast<const uint8_t*>(feat) + row0 * 16, bytes, bar(BAR_X_FULL + s));
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer (one thread) ============================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc_l1 = make_idesc(128, 64), idesc_128 = make_idesc(128, 128);
+            mbar_wait(bar(BAR_W_FULL), 0);
+            tc_fence_after();
+            auto issue_l3 = [&](int it, int cb) {           // layer 3, channel block cb of tile `it`
+                const int q = it * 4 + cb, b = cb & 1, buf = it & 1;
+                if (cb == 0) { mbar_wait(bar(BAR_A3_FULL + buf), (it >> 1) & 1); }
+                mbar_wait(bar(BAR_D3_EMPTY + b), ((q >> 1) & 1) ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t kb = k >> 2, kk = k & 3;
+                    const uint64_t da = make_desc(sbase + kSmW3 + (cb * 2 + kb) * 16384 + kk * 32, 16, 1024, kLayoutSw128);
+                    const uint64_t db = make_desc(sbase + kSmA3 + buf * 32768 + kb * 16384 + kk * 32, 16, 1024, kLayoutSw128);
+                    tc_mma(tmem + kColD3 + b * 128, da, db, idesc_128, k > 0);
+                }
+                tc_commit(bar(BAR_D3_FULL + b));
+                if (cb == 3) tc_commit(bar(BAR_A3_EMPTY + buf));
+            };
+            for (int i = 0; i <= total; ++i) {
+                if (i < total) {
+                    const int s = i % kStages;
+                    mbar_wait(bar(BAR_X_FULL + s), (i / kStages) & 1);
+                    tc_fence_after();
+                    const uint32_t xa = sbase + kSmX + s * 2048;
+                    const uint64_t da = make_desc(xa, (sbase + kSmZero) - xa, 128, kLayoutNone);
+                    const uint64_t db = make_desc(sbase + kSmW1, 1024, 128, kLayoutNone);
+                    tc_mma(tmem + kColD1, da, db, idesc_l1, 0);
+                    tc_commit(bar(BAR_X_EMPTY + s));
+                    tc_commit(bar(BAR_D1_FULL));
+                }
+                if (i >= 1) { issue_l3(i - 1, 0); issue_l3(i - 1, 1); }
+                if (i < total) {
+                    mbar_wait(bar(BAR_A2_FULL), i & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t da = make_desc(sbase + kSmA3 + (i & 1) * 32768 + kk * 32, 16, 1024, kLayoutSw128);
+                        const uint64_t db = make_desc(sbase + kSmW2 + kk * 32, 16, 1024, kLayoutSw128);
+                        tc_mma(tmem + kColD2, da, db, idesc_128, kk > 0);
+                    }
+                    tc_commit(bar(BAR_D2_FULL));
+                }
+                if (i >= 1) { issue_l3(i - 1, 2); issue_l3(i - 1, 3); }
+            }
+        }
+    } else if (warp < 4) {
+        // ===== front epilogues: D1 -> H1 (bf16, swizzled), D2 -> H2 ================================
+        const uint32_t r = (uint32_t)tid;                               // TMEM lane = point row of the tile
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const float* b1 = reinterpret_cast<const float*>(sm + kSmB1);
+        const float* b2 = reinterpret_cast<const float*>(sm + kSmB2);
+        for (int i = 0; i < total; ++i) {
+            const int buf = i & 1, j = i / T, tt = i - j * T;
+            const long long row0 = (long long)(pair + j * n_pairs) * N + (long long)tt * kTile;
+            const int valid = min(kTile, N - tt * kTile);
+            uint8_t* a3 = sm + kSmA3 + buf * 32768;
+            mbar_wait(bar(BAR_A3_EMPTY + buf), ((i >> 1) & 1) ^ 1);     // layer 3 of tile i-2 has released this buffer
+            mbar_wait(bar(BAR_D1_FULL), i & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {                               // 2 x 32 channels
+                uint32_t v[32];
+                tc_ld32(lane_addr + kColD1 + g * 32, v);
+                tc_wait_ld();
+                float f[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) f[c] = fmaxf(__uint_as_float(v[c]) + b1[g * 32 + c], 0.f);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint4 o;
+                    o.x = pack2(f[c8 * 8 + 0], f[c8 * 8 + 1]); o.y = pack2(f[c8 * 8 + 2], f[c8 * 8 + 3]);
+                    o.z = pack2(f[c8 * 8 + 4], f[c8 * 8 + 5]); o.w = pack2(f[c8 * 8 + 6], f[c8 * 8 + 7]);
+                    *reinterpret_cast<uint4*>(a3 + sw128_off(r, g * 4 + c8)) = o;
+                }
+                if (dbg_h1 && half == 0 && (int)r < valid)
+                    for (int c = 0; c < 32; ++c)
+                        dbg_h1[(row0 + r) * 64 + g * 32 + c] = __bfloat162float(__float2bfloat16_rn(f[c]));
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar(1, 128);
+            if (tid == 0) mbar_arrive(bar(BAR_A2_FULL));
+
+            mbar_wait(bar(BAR_D2_FULL), i & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {                               // 4 x 32 channels
+                uint32_t v[32];
+                tc_ld32(lane_addr + kColD2 + g * 32, v);
+                tc_wait_ld();
+                float f[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) f[c] = fmaxf(__uint_as_float(v[c]) + b2[g * 32 + c], 0.f);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint4 o;
+                    o.x = pack2(f[c8 * 8 + 0], f[c8 * 8 + 1]); o.y = pack2(f[c8 * 8 + 2], f[c8 * 8 + 3]);
+                    o.z = pack2(f[c8 * 8 + 4], f[c8 * 8 + 5]); o.w = pack2(f[c8 * 8 + 6], f[c8 * 8 + 7]);
+                    const uint32_t chunk = g * 4 + c8;                  // 0..15 over K = 128
+                    *reinterpret_cast<uint4*>(a3 + (chunk >> 3) * 16384 + sw128_off(r, chunk & 7)) = o;
+                }
+                if (dbg_h2 && half == 0 && (int)r < valid)
+                    for (int c = 0; c < 32; ++c)
+                        dbg_h2[(row0 + r) * 128 + g * 32 + c] = __bfloat162float(__float2bfloat16_rn(f[c]));
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar(1, 128);
+            if (tid == 0) mbar_arrive(bar(BAR_A3_FULL + buf));
+        }
+    } else {
+        // ===== max-pool epilogue: D3[channel lane][point column] -> running max -> pooled ===========
+        const int wq = warp - 4;                                        // TMEM lane quadrant == warp % 4
+        const int L = wq * 32 + lane;                                   // channel within the 128-channel block
+        const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int i = 0; i < total; ++i) {
+            const int j = i / T, tt = i - j * T;
+            const int h = pair + j * n_pairs;
+            const int valid = min(kTile, N - tt * kTile);
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                const int q = i * 4 + cb, b = cb & 1;
+                mbar_wait(bar(BAR_D3_FULL + b), (q >> 1) & 1);
+                tc_fence_after();
+                float mm = m[cb];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t v[32];
+                    tc_ld32(lane_addr + kColD3 + b * 128 + g * 32, v);
+                    tc_wait_ld();
+                    if (valid == kTile) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) mm = fmaxf(mm, __uint_as_float(v[c]));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (g * 32 + c < valid) mm = fmaxf(mm, __uint_as_float(v[c]));
+                    }
+                }
+                tc_fence_before();
+                named_bar(2, 128);
+                if (tid == 128) mbar_arrive(bar(BAR_D3_EMPTY + b));
+                if (tt == T - 1) {
+                    const int ch = half * 512 + cb * 128 + L;
+                    pooled[(size_t)h * 1024 + ch] = fmaxf(mm + __ldg(wf32 + ZS_OFF_B3 + ch), 0.f);
+                    mm = -INFINITY;
+                }
+                m[cb] = mm;
+            }
+        }
+    }
+
+    // ---- teardown --------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- weight images -------------------------------------------------------------------------------
+// Writes the bf16 operand images exactly as they sit in shared memory (see the map above).
+__global__ void zs_k_build_images(const float* __restrict__ w, uint8_t* __restrict__ img) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // W3: 1024 x 128
+    if (i < 1024 * 128) {
+        const int ch = i >> 7, k = i & 127;
+        const int half = ch >> 9, cb = (ch >> 7) & 3, mrow = ch & 127, kb = k >> 6, kc = k & 63;
+        const size_t off = (size_t)half * kImgW3Half + (size_t)(cb * 2 + kb) * 16384 + sw128_off(mrow, kc >> 3) + (kc & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(w[ZS_OFF_W3 + i]);
+    }
+    // W2: 128 x 64
+    if (i < 128 * 64) {
+        const int ch = i >> 6, k = i & 63;
+        *reinterpret_cast<__nv_bfloat16*>(img + kImgW2 + sw128_off(ch, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(w[ZS_OFF_W2 + i]);
+    }
+    // W1: 64 x 16 (K 8..15 zero), no swizzle: chunk-major core matrices
+    if (i < 64 * 16) {
+        const int ch = i >> 4, k = i & 15;
+        const size_t off = (size_t)(k >> 3) * 1024 + (size_t)(ch >> 3) * 128 + (ch & 7) * 16 + (k & 7) * 2;
+        const float v = k < 8 ? w[ZS_OFF_W1 + ch * 8 + k] : 0.f;
+        *reinterpret_cast<__nv_bfloat16*>(img + kImgW1 + off) = __float2bfloat16_rn(v);
+    }
+}
+
+}  // namespace
+
+int zs_tc_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st) {
+    zs_weights& w = ctx->w[slot];
+    if (!w.bf16 && cudaMalloc(&w.bf16, kImgBytes) != cudaSuccess) {
+        cudaGetLastError();
+        return zs_fail(ctx, ZS_ERR_NOMEM, "bf16 weight images");
+    }
+    zs_k_build_images<<<(1024 * 128 + 255) / 256, 256, 0, st>>>(w.f32, reinterpret_cast<uint8_t*>(w.bf16));
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
 void zs_tc_destroy(zs_ctx*) {}
-int zs_score_tc(zs_ctx* ctx, int, const __nv_bfloat16*, int, int, float*, cudaStream_t) {
-    return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "bf16 tensor-core scorer not built yet");
+
+static int launch_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, int n_pts, float* pooled,
+                     float* dbg_h1, float* dbg_h2, cudaStream_t st) {
+    const zs_weights& w = ctx->w[slot];
+    ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmAlloc));
+    int grid = ctx->sm_count & ~1;                 // CTA pairs
+    if (grid > 2 * n) grid = 2 * n;
+    zs_k_mlp_tc<<<grid, kThreadsTc, kSmAlloc, st>>>(feat, n, n_pts, reinterpret_cast<const uint8_t*>(w.bf16), w.f32,
+                                                     pooled, dbg_h1, dbg_h2);
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
+int zs_score_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, int n_pts, float* pooled, cudaStream_t st) {
+    return launch_tc(ctx, slot, feat, n, n_pts, pooled, nullptr, nullptr, st);
+}
+
+// Diagnostic entry point: as zs_pool (bf16) but also dumps the bf16-rounded activations of layers 1 and 2.
+extern "C" int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat_bf16, int n, int n_pts, float* pooled_out,
+                             float* h1_out, float* h2_out, void* stream) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (weight_slot < 0 || weight_slot >= ZS_MAX_WEIGHT_SLOTS || !ctx->w[weight_slot].set)
+        return zs_fail(ctx, ZS_ERR_STATE, "weight slot %d not set", weight_slot);
+    if (n <= 0 || n_pts <= 0 || !feat_bf16 || !pooled_out) return zs_fail(ctx, ZS_ERR_INVALID, "zs_pool_debug arguments");
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_tc(ctx, weight_slot, (const __nv_bfloat16*)feat_bf16, n, n_pts, pooled_out, h1_out, h2_out, (cudaStream_t)stream);
 }

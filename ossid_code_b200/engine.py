@@ -207,6 +207,16 @@ class ZsContext:
         self._ck(self.lib.zs_head(self.h, wslot, pooled.data_ptr(), n, scores.data_ptr(), self._stream()), "zs_head")
         return scores
 
+    def pool_debug(self, wslot: int, feat: torch.Tensor):
+        """Tensor-core pool plus the bf16-rounded layer-1 / layer-2 activations (diagnostic)."""
+        n, N = feat.shape[0], feat.shape[1]
+        pooled = torch.zeros((n, 1024), dtype=torch.float32, device=self.device)
+        h1 = torch.zeros((n * N, 64), dtype=torch.float32, device=self.device)
+        h2 = torch.zeros((n * N, 128), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.zs_pool_debug(self.h, wslot, feat.data_ptr(), n, N, pooled.data_ptr(), h1.data_ptr(),
+                                        h2.data_ptr(), self._stream()), "zs_pool_debug")
+        return pooled, h1.view(n, N, 64), h2.view(n, N, 128)
+
     def topk(self, scores: torch.Tensor, k: int, index_base: int = 0):
         s = torch.empty((k,), dtype=torch.float32, device=self.device)
         i = torch.empty((k,), dtype=torch.int32, device=self.device)

@@ -284,3 +284,51 @@ def test_full_size_properties(ctx):
     assert float((scores[sl].cpu() - rs).abs().max()) <= _score_tol(rs, SCORE_F32_RTOL) + 1e-6
     ts, ti = ctx.topk(scores, 8)
     assert int(ti[0]) == int(torch.argmax(scores))
+
+
+# --- tensor-core scorer (tcgen05) -------------------------------------------------------------------
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _oracle_layers_bf16(x_bf16, w):
+    """bf16-emulated layer outputs exactly as oracle.scorer(bf16=True) computes them."""
+    x = x_bf16.to(torch.float32)
+    h1 = _bf(torch.relu(x @ _bf(w["W1"]).T + w["b1"]))
+    h2 = _bf(torch.relu(h1 @ _bf(w["W2"]).T + w["b2"]))
+    h3 = torch.relu(h2 @ _bf(w["W3"]).T + w["b3"])
+    return h1, h2, h3.max(dim=1).values
+
+
+@pytest.mark.parametrize("n,N", [(1, 128), (2, 256), (3, 100), (5, 1000), (150, 130), (1, 1), (40, 1000)])
+def test_tc_scorer_layers_match_bf16_oracle(ctx, n, N):
+    """tcgen05 path layer by layer vs the bf16-emulating oracle (tight), then end scores vs fp32 oracle (1e-2)."""
+    g = torch.Generator().manual_seed(7 * n + N)
+    x = (torch.randn(n, N, 8, generator=g) * 0.5).to(torch.bfloat16)
+    w = weights.seeded_folded(2)
+    ctx.set_weights(1, w)
+    pooled, h1, h2 = ctx.pool_debug(1, x.to(ctx.device))
+    r1, r2, rp = _oracle_layers_bf16(x, w)
+    e1 = float((h1.cpu() - r1).abs().max()); e2 = float((h2.cpu() - r2).abs().max())
+    ep = float((pooled.cpu() - rp).abs().max())
+    print(f"n={n} N={N}: max|dh1|={e1:.3e} (scale {float(r1.abs().max()):.2f}) max|dh2|={e2:.3e} "
+          f"(scale {float(r2.abs().max()):.2f}) max|dpool|={ep:.3e} (scale {float(rp.abs().max()):.2f})")
+    # one bf16 ulp of slack per layer for accumulation-order differences at rounding boundaries
+    assert e1 <= 2 ** -7 * float(r1.abs().max()) + 1e-6, "layer 1 (X . W1^T) differs"
+    assert e2 <= 2 ** -6 * float(r2.abs().max()) + 1e-6, "layer 2 (H1 . W2^T) differs"
+    assert ep <= 2 ** -5 * float(rp.abs().max()) + 1e-6, "layer 3 + max-pool differs"
+    scores = ctx.score(1, x.to(ctx.device)).cpu()
+    ref32 = zo.scorer(x.to(torch.float32), w)
+    refbf = zo.scorer(x.to(torch.float32), w, bf16=True)
+    assert float((scores - refbf).abs().max()) <= 2e-3 * float(refbf.abs().max()) + 1e-6
+    assert float((scores - ref32).abs().max()) <= SCORE_BF16_RTOL * float(ref32.abs().max()) + 1e-6
+
+
+def test_tc_scorer_batch_position_invariance(ctx):
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(300, 1000, 8, generator=g) * 0.5).to(torch.bfloat16).to(ctx.device)
+    ctx.set_weights(1, weights.seeded_folded(2))
+    s = ctx.score(1, x)
+    perm = torch.randperm(300, generator=g).to(ctx.device)
+    assert torch.equal(ctx.score(1, x[perm].contiguous()), s[perm]), "tensor-core scores depend on batch position"
+    assert torch.equal(ctx.score(1, x[:7].contiguous()), s[:7])

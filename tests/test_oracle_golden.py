@@ -139,7 +139,7 @@ def test_features_scalar_recomputation():
                     nrm = np.sqrt(f32(f32(x * x + y * y) + z * z)) * np.sqrt(f32(f32(n3[0] ** 2 + n3[1] ** 2) + n3[2] ** 2))
                     nc = f32(dot / nrm)
                     exp[:] = [f32(f32(u) - cx) * ifx, f32(f32(v) - cy) * ify, dH, ho[1] - hm[1], ho[2] - hm[2], dD,
-                              0 if np.isnan(nc) else nc, 0]
+                              nc if np.isfinite(nc) else 0, 0]
                 assert int(f["mask"][h, p]) == mk
                 assert f["uv"][h, p].tolist() == [u, v]
                 np.testing.assert_allclose(f["point_x"][h, p].numpy(), exp, rtol=1e-6, atol=1e-7)
