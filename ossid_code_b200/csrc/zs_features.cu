@@ -16,6 +16,7 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
+constexpr float kFltMax = 3.402823466e38f;   // 0 < z <= FLT_MAX, i.e. finite (oracle: z < inf)
 
 struct obj_view {
     const float4* pA;
@@ -92,7 +93,7 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
                 float x, y, z, ur, vr;
                 zs_transform(T, a.x, a.y, a.z, x, y, z);
                 zs_project(cam, x, y, z, ur, vr);
-                const bool valid = (z > 0.f) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
+                const bool valid = (z > 0.f) && (z <= kFltMax) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
                 // R.n, same association as the points (no translation)
                 const float nx = xdot3(T.r[0], T.r[1], T.r[2], b.x, b.y, b.z);
                 const float ny = xdot3(T.r[4], T.r[5], T.r[6], b.x, b.y, b.z);
@@ -103,7 +104,7 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
                     ui = (int)ur;
                     vi = (int)vr;
                     const float4 px = __ldg(frame + (size_t)vi * cam.W + ui);   // {d_obs, H, S, V}
-                    const bool vd = px.x > 0.f;
+                    const bool vd = (px.x > 0.f) && (px.x <= kFltMax);
                     const float dD = vd ? xsub(px.x, z) : 0.f;
                     mk |= ZS_BIT_VALID_PROJ | (vd ? ZS_BIT_VALID_DEPTH : 0);
                     if (vd && dD > ZS_DEPTH_MARGIN) mk |= ZS_BIT_FREE_SPACE;
@@ -120,7 +121,7 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
                     // cos of the angle between the viewing ray and the rotated normal
                     // (python/ossid/datasets/ycbv_object.py:74); 1e-4 feature, so rsqrt is fine
                     const float c = dot * rsqrtf(x * x + y * y + z * z) * rsqrtf(nx * nx + ny * ny + nz * nz);
-                    f6 = (fabsf(c) <= 3.402823466e38f) ? c : 0.f;      // NaN / inf (degenerate pose) -> 0
+                    f6 = (fabsf(c) <= kFltMax) ? c : 0.f;      // NaN / inf (degenerate pose) -> 0
                 }
             }
             viol += __popc(__ballot_sync(0xffffffffu, (mk & ZS_BIT_FREE_SPACE) != 0));
@@ -171,9 +172,9 @@ zs_k_violations(obj_view o, zs_cam cam, const float4* __restrict__ frame, const 
                 float x, y, z, ur, vr;
                 zs_transform(T, a.x, a.y, a.z, x, y, z);
                 zs_project(cam, x, y, z, ur, vr);
-                if ((z > 0.f) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH)) {
+                if ((z > 0.f) && (z <= kFltMax) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH)) {
                     const float d = __ldg(frame_d + 4 * ((size_t)(int)vr * cam.W + (int)ur));
-                    fs = (d > 0.f) && (xsub(d, z) > ZS_DEPTH_MARGIN);
+                    fs = (d > 0.f) && (d <= kFltMax) && (xsub(d, z) > ZS_DEPTH_MARGIN);
                 }
             }
             viol += __popc(__ballot_sync(0xffffffffu, fs));
@@ -319,11 +320,11 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
                            int32_t* viol_out, void* stream) {
     obj_view o;
     zs_cam cam;
+    if (ctx && n_keep == 0) return ZS_OK;
     int rc = check_obj(ctx, obj_slot, poses, o, cam);
     if (rc) return rc;
     if (n_keep < 0 || (feat_dtype != ZS_F32 && feat_dtype != ZS_BF16))
         return zs_fail(ctx, ZS_ERR_INVALID, "n_keep %d, feat_dtype %d", n_keep, feat_dtype);
-    if (n_keep == 0) return ZS_OK;
     if (!feat_out || ((uintptr_t)feat_out & 15) || (uv_out && ((uintptr_t)uv_out & 7)))
         return zs_fail(ctx, ZS_ERR_INVALID, "feat_out must be 16-byte aligned (uv_out 8)");
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -350,10 +351,10 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
 extern "C" int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, int32_t* viol_out, void* stream) {
     obj_view o;
     zs_cam cam;
+    if (ctx && n == 0) return ZS_OK;
     int rc = check_obj(ctx, obj_slot, poses, o, cam);
     if (rc) return rc;
-    if (n < 0 || (n > 0 && !viol_out)) return zs_fail(ctx, ZS_ERR_INVALID, "n %d", n);
-    if (n == 0) return ZS_OK;
+    if (n < 0 || !viol_out) return zs_fail(ctx, ZS_ERR_INVALID, "n %d", n);
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t smem = (size_t)o.n_pts * 36;
     const bool in_smem = smem <= kCloudSmemMax;
@@ -386,10 +387,10 @@ static int project_common(zs_ctx* ctx, const float* poses, int n, const float* p
                           float fx, float fy, float cx, float cy, int H, int W, int32_t* uv_out,
                           const uint8_t* mask, int32_t* count_out, void* stream) {
     if (!ctx) return ZS_ERR_INVALID;
+    if (n == 0) return ZS_OK;
     if (n < 0 || n_pts <= 0 || !pts || !poses || ((uintptr_t)poses & 15))
         return zs_fail(ctx, ZS_ERR_INVALID, "projection arguments");
     if ((size_t)n_pts * 12 > kCloudSmemMax) return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "%d model points", n_pts);
-    if (n == 0) return ZS_OK;
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     zs_cam cam{fx, fy, cx, cy, 0.f, 0.f, H, W};
     const size_t smem = (size_t)n_pts * 12;

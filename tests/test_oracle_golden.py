@@ -118,7 +118,7 @@ def test_features_scalar_recomputation():
                 x, y, z = (f32(v) for v in xyz)
                 ur = np.rint(f32(f32(x / z) * fx) + cx)
                 vr = np.rint(f32(f32(y / z) * fy) + cy)
-                valid = bool(z > 0 and 0 <= ur < W and 0 <= vr < H)
+                valid = bool(0 < z < np.inf and 0 <= ur < W and 0 <= vr < H)
                 dot = -f32(f32(f32(x * n3[0]) + f32(y * n3[1])) + f32(z * n3[2]))
                 mk = (zo.BIT_FRONT if dot > 0 else 0)
                 exp = np.zeros(8, np.float32)
@@ -127,7 +127,7 @@ def test_features_scalar_recomputation():
                     n_valid += 1
                     u, v = int(ur), int(vr)
                     d = dep[v, u]
-                    vd = bool(d > 0)
+                    vd = bool(0 < d < np.inf)
                     dD = f32(d - z) if vd else f32(0)
                     mk |= zo.BIT_VALID_PROJ | (zo.BIT_VALID_DEPTH if vd else 0)
                     mk |= zo.BIT_FREE_SPACE if (vd and dD > f32(0.02)) else 0
