@@ -135,10 +135,12 @@ ZS_API int zs_score(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dty
 
 /* The two halves of zs_score, exposed so that callers can keep the pooled vectors and so that
  * each stage can be timed alone: zs_pool = shared per-point MLP + max over points
- * (pooled_out [dev] float32 [n][1024]); zs_head = 1024 -> 512 -> 256 -> 1 (fp32). */
+ * (pooled_out [dev] float32 [n][1024]); zs_head = 1024 -> 512 -> 256 -> 1, precision ZS_F32: fp32 on
+ * CUDA cores (1e-4 parity path), ZS_BF16: tf32 tensor cores (what zs_score uses after the bf16 MLP). */
 ZS_API int zs_pool(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtype, int n, int n_pts,
             float* pooled_out, void* stream);
-ZS_API int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n, float* scores_out, void* stream);
+ZS_API int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n, int precision, float* scores_out,
+            void* stream);
 
 /* Diagnostic twin of zs_pool for bf16 features: additionally dumps the bf16-rounded activations
  * of layers 1 and 2 (h1_out [dev] float32 [n*n_pts][64], h2_out [dev] float32 [n*n_pts][128];
@@ -148,9 +150,10 @@ ZS_API int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat_bf16, in
 
 /* Per-object top-k, ordered by (score desc, index asc); k <= ZS_MAX_TOPK.  Generalises
  * `scores.argmax()` (online_learning.py:466-467; first maximum wins ties).
- * s_out [dev] float32 [k], i_out [dev] int32 [k] (= local index + index_base); entries
- * beyond n are (-inf, -1). */
-ZS_API int zs_topk(zs_ctx* ctx, const float* scores, int n, int k, int index_base,
+ * s_out [dev] float32 [k], i_out [dev] int32 [k] = index_map[i] + index_base (index_map [dev] int32 [n],
+ * NULL = identity; pass zs_filter's keep_idx to get indices into the unfiltered hypothesis list);
+ * entries beyond n are (-inf, -1). */
+ZS_API int zs_topk(zs_ctx* ctx, const float* scores, int n, int k, int index_base, const int32_t* index_map,
             float* s_out, int32_t* i_out, void* stream);
 
 #ifdef __cplusplus

@@ -32,9 +32,9 @@ SIGNATURES = {
     "zs_features": (_i, [_p, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
     "zs_score": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p]),
     "zs_pool": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
-    "zs_head": (_i, [_p, _i, _p, _i, _p, _p]),
+    "zs_head": (_i, [_p, _i, _p, _i, _i, _p, _p]),
     "zs_pool_debug": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p]),
-    "zs_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "zs_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -66,6 +66,7 @@ int zs_reserve_ws(zs_ctx* ctx, size_t bytes);
 int zs_tc_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);   // zs_score_tc.cu
 void zs_tc_destroy(zs_ctx* ctx);
 int zs_score_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, int n_pts, float* pooled, cudaStream_t st);
+int zs_head_tc(zs_ctx* ctx, int slot, const float* pooled, int n, float* scores, float* g1, cudaStream_t st);  // zs_head_tc.cu
 int zs_f32_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);  // zs_score_f32.cu
 
 #define ZS_CUDA(ctx, call)                                                                      \

@@ -1,0 +1,236 @@
+// Head of the scorer on tensor cores: pooled[n][1024] -> fc1(512)+ReLU -> fc2(256)+ReLU -> fc3(1).
+// Used by the tensor-core scoring path; the fp32 CUDA-core head (zs_score_f32.cu) stays the 1e-4
+// parity path.  Reference call: model({"point_x": ...}), python/ossid/utils/zephyr_utils.py:34.
+//
+// One generic kernel, out[n][CO] = relu(A[n][K] . W[CO][K]^T + b), kind::tf32 (fp32 operands read
+// straight from the fp32 buffers, 10-bit mantissa in the multiplier, fp32 accumulate in TMEM):
+//   * CTA tile 128 rows x 256 output channels, K walked in blocks of 32 floats (= one 128-byte
+//     swizzle row); A and W tiles arrive by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) through a
+//     4-stage mbarrier ring; 4 MMAs (M=128, N=256, K=8) per block issued by one thread.
+//   * warps: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-5 = epilogue (thread = row).
+//   * fc2's epilogue folds fc3 in: each thread owns all 256 hidden values of its hypothesis and
+//     reduces them against F3 in registers, so only one float per hypothesis is written.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "zs_common.cuh"
+
+namespace {
+
+constexpr int kThreadsFc = 192;
+constexpr int kFcStages = 4;
+constexpr int kBM = 128, kBN = 256, kBK = 32;                 // rows, output channels, floats per k-block
+constexpr uint32_t kStageA = kBM * kBK * 4;                   // 16 KB
+constexpr uint32_t kStageW = kBN * kBK * 4;                   // 32 KB
+constexpr uint32_t kStageBytes = kStageA + kStageW;           // 48 KB
+constexpr uint32_t kFcBar = kFcStages * kStageBytes;          // barriers after the ring
+constexpr uint32_t kFcTmemPtr = kFcBar + 128;
+constexpr uint32_t kFcSmAlloc = kFcTmemPtr + 16 + 1024;
+static_assert(kFcSmAlloc <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+// K-major, 128-byte-swizzled operand descriptor (8-row groups 1024 B apart), version 1
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// fp32 accumulate, tf32 x tf32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kFuseOut: instead of storing relu(acc + b), reduce it against `f3` and store one score per row.
+template <bool kFuseOut>
+__global__ void __launch_bounds__(kThreadsFc, 1)
+zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+           const float* __restrict__ bias, float* __restrict__ out, int n, int K, int CO,
+           const float* __restrict__ f3, const float* __restrict__ c3) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
+    auto full = [&](int s) { return sbase + kFcBar + 8u * (uint32_t)s; };
+    auto empty = [&](int s) { return sbase + kFcBar + 8u * (uint32_t)(kFcStages + s); };
+    const uint32_t acc_full = sbase + kFcBar + 8u * (2 * kFcStages);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int co0 = blockIdx.x * kBN, row0 = blockIdx.y * kBM;
+    const int n_kb = K / kBK;
+
+    if (tid == 0) {
+        for (int s = 0; s < kFcStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kFcTmemPtr), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kFcTmemPtr);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % kFcStages;
+                mbar_wait(empty(s), ((kb / kFcStages) & 1) ^ 1);
+                mbar_expect_tx(full(s), kStageBytes);
+                tma_load_2d(sbase + s * kStageBytes, &map_a, kb * kBK, row0, full(s));
+                tma_load_2d(sbase + s * kStageBytes + kStageA, &map_w, kb * kBK, co0, full(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(kBM, kBN);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % kFcStages;
+                mbar_wait(full(s), (kb / kFcStages) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {              // 4 x (K = 8 floats = 32 bytes)
+                    const uint64_t da = make_desc_sw128(sbase + s * kStageBytes + kk * 32);
+                    const uint64_t db = make_desc_sw128(sbase + s * kStageBytes + kStageA + kk * 32);
+                    tc_mma_tf32(tmem, da, db, idesc, (kb | kk) != 0);
+                }
+                tc_commit(empty(s));
+            }
+            tc_commit(acc_full);
+        }
+    } else {
+        const int q = warp & 3;                               // TMEM lane quadrant this warp may read
+        const int row = row0 + q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        float dot = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < kBN / 64; ++g) {
+            uint32_t v0[32], v1[32];
+            tc_ld32(lane_addr + g * 64, v0);
+            tc_ld32(lane_addr + g * 64 + 32, v1);
+            tc_wait_ld();
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const uint32_t(&v)[32] = hlf ? v1 : v0;
+                const int c0 = co0 + g * 64 + hlf * 32;
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + c));
+                    float4 o;
+                    o.x = fmaxf(__uint_as_float(v[c + 0]) + b.x, 0.f); o.y = fmaxf(__uint_as_float(v[c + 1]) + b.y, 0.f);
+                    o.z = fmaxf(__uint_as_float(v[c + 2]) + b.z, 0.f); o.w = fmaxf(__uint_as_float(v[c + 3]) + b.w, 0.f);
+                    if (kFuseOut) {
+                        const float4 f = __ldg(reinterpret_cast<const float4*>(f3 + c0 + c));
+                        dot = fmaf(o.x, f.x, dot); dot = fmaf(o.y, f.y, dot);
+                        dot = fmaf(o.z, f.z, dot); dot = fmaf(o.w, f.w, dot);
+                    } else if (row < n) {
+                        *reinterpret_cast<float4*>(out + (size_t)row * CO + c0 + c) = o;
+                    }
+                }
+            }
+        }
+        if (kFuseOut && row < n) out[row] = dot + __ldg(c3);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int get_encoder(zs_ctx* ctx) {
+    if (g_encode) return ZS_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return zs_fail(ctx, ZS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return ZS_OK;
+}
+
+// fp32 row-major [rows][K] matrix, box = [box_rows][32 floats], 128-byte swizzle, OOB rows read as zero
+int make_map(zs_ctx* ctx, CUtensorMap* map, const float* base, int rows, int K, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return zs_fail(ctx, ZS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows %d K %d", (int)r, rows, K);
+    return ZS_OK;
+}
+
+}  // namespace
+
+// pooled [n][1024] -> scores [n]; g1 [n][512] scratch.  Weights: the fp32 blob of zs_set_weights.
+int zs_head_tc(zs_ctx* ctx, int slot, const float* pooled, int n, float* scores, float* g1, cudaStream_t st) {
+    int rc = get_encoder(ctx);
+    if (rc) return rc;
+    const zs_weights& w = ctx->w[slot];
+    CUtensorMap a1, w1, a2, w2;
+    if ((rc = make_map(ctx, &a1, pooled, n, 1024, kBM)) || (rc = make_map(ctx, &w1, w.f32 + ZS_OFF_F1, 512, 1024, kBN)) ||
+        (rc = make_map(ctx, &a2, g1, n, 512, kBM)) || (rc = make_map(ctx, &w2, w.f32 + ZS_OFF_F2, 256, 512, kBN)))
+        return rc;
+    ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_fc_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcSmAlloc));
+    ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_fc_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcSmAlloc));
+    const int row_tiles = (n + kBM - 1) / kBM;
+    zs_k_fc_tc<false><<<dim3(512 / kBN, row_tiles), kThreadsFc, kFcSmAlloc, st>>>(a1, w1, w.f32 + ZS_OFF_C1, g1, n, 1024, 512,
+                                                                               nullptr, nullptr);
+    ZS_LAUNCHED(ctx);
+    zs_k_fc_tc<true><<<dim3(256 / kBN, row_tiles), kThreadsFc, kFcSmAlloc, st>>>(a2, w2, w.f32 + ZS_OFF_C2, scores, n, 512, 256,
+                                                                              w.f32 + ZS_OFF_F3, w.f32 + ZS_OFF_C3);
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}

@@ -211,7 +211,9 @@ int zs_f32_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st) {
 }
 
 // pooled [m][1024] -> scores [m]; g1 [m][512], g2 [m][256] scratch.
-static int head_impl(zs_ctx* ctx, int slot, const float* pooled, int n, float* scores, float* g1, float* g2, cudaStream_t st) {
+static int head_impl(zs_ctx* ctx, int slot, const float* pooled, int n, float* scores, float* g1, float* g2,
+                     int precision, cudaStream_t st) {
+    if (precision == ZS_BF16) return zs_head_tc(ctx, slot, pooled, n, scores, g1, st);   // tensor cores (tf32)
     const zs_weights& w = ctx->w[slot];
     dim3 g_fc1((n + kRows - 1) / kRows, 512 / 128), g_fc2((n + kRows - 1) / kRows, 256 / 128);
     zs_k_fc<true><<<g_fc1, kThreadsMlp, 0, st>>>(pooled, w.f32t + kOffF1t, w.f32 + ZS_OFF_C1, g1, n, 1024, 512);
@@ -258,11 +260,12 @@ extern "C" int zs_pool(zs_ctx* ctx, int weight_slot, const void* feat, int feat_
     return pool_impl(ctx, weight_slot, feat, feat_dtype, n, n_pts, pooled_out, (cudaStream_t)stream);
 }
 
-extern "C" int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n, float* scores_out, void* stream) {
+extern "C" int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n, int precision, float* scores_out,
+                       void* stream) {
     if (!ctx) return ZS_ERR_INVALID;
     if (weight_slot < 0 || weight_slot >= ZS_MAX_WEIGHT_SLOTS || !ctx->w[weight_slot].set)
         return zs_fail(ctx, ZS_ERR_STATE, "weight slot %d not set", weight_slot);
-    if (n < 0 || (n > 0 && (!pooled || !scores_out || ((uintptr_t)pooled & 15))))
+    if (n < 0 || (precision != ZS_F32 && precision != ZS_BF16) || (n > 0 && (!pooled || !scores_out || ((uintptr_t)pooled & 15))))
         return zs_fail(ctx, ZS_ERR_INVALID, "zs_head arguments");
     if (n == 0) return ZS_OK;
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -273,7 +276,7 @@ extern "C" int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n,
     float* g2 = g1 + (size_t)chunk * 512;
     for (int s = 0; s < n; s += chunk) {
         const int m = (n - s) < chunk ? (n - s) : chunk;
-        rc = head_impl(ctx, weight_slot, pooled + (size_t)s * 1024, m, scores_out + s, g1, g2, (cudaStream_t)stream);
+        rc = head_impl(ctx, weight_slot, pooled + (size_t)s * 1024, m, scores_out + s, g1, g2, precision, (cudaStream_t)stream);
         if (rc) return rc;
     }
     return ZS_OK;
@@ -300,7 +303,7 @@ extern "C" int zs_score(zs_ctx* ctx, int weight_slot, const void* feat, int feat
         const int m = (n - s) < chunk ? (n - s) : chunk;
         rc = pool_impl(ctx, weight_slot, (const char*)feat + (size_t)s * n_pts * 8 * esz, feat_dtype, m, n_pts, pooled, st);
         if (rc) return rc;
-        rc = head_impl(ctx, weight_slot, pooled, m, scores_out + s, g1, g2, st);
+        rc = head_impl(ctx, weight_slot, pooled, m, scores_out + s, g1, g2, precision, st);
         if (rc) return rc;
     }
     return ZS_OK;

@@ -127,13 +127,60 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// byte offset of 16-byte chunk `c` (8 bf16) of row `r` in a [rows x 64 bf16] 128B-swizzled K-major tile
+__host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c) { return r * 128u + (((c ^ (r & 7u)) & 7u) << 4); }
+
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ float max3(float a, float b, float c) {      // FMNMX3
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// bf16x2( relu(a0 + b0), relu(a1 + b1) ): one FADD2 + one F2FP.RELU.BF16.PACK_AB for two channels
+__device__ __forceinline__ uint32_t bias_relu_pack(uint32_t a0, uint32_t a1, float2 b) {
+    uint64_t acc, bias, sum;
+    uint32_t r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(acc) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(bias) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(sum) : "l"(acc), "l"(bias));
+    float lo, hi;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(sum));
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// 32 accumulator columns of one point -> 4 swizzled 16-byte chunks of the next layer's operand row
+__device__ __forceinline__ void epi_store32(const uint32_t (&v)[32], const float* __restrict__ bias, uint8_t* tile,
+                                            uint32_t r, uint32_t chunk0) {
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+        const float4 bA = *reinterpret_cast<const float4*>(bias + c8 * 8);
+        const float4 bB = *reinterpret_cast<const float4*>(bias + c8 * 8 + 4);
+        uint4 o;
+        o.x = bias_relu_pack(v[c8 * 8 + 0], v[c8 * 8 + 1], make_float2(bA.x, bA.y));
+        o.y = bias_relu_pack(v[c8 * 8 + 2], v[c8 * 8 + 3], make_float2(bA.z, bA.w));
+        o.z = bias_relu_pack(v[c8 * 8 + 4], v[c8 * 8 + 5], make_float2(bB.x, bB.y));
+        o.w = bias_relu_pack(v[c8 * 8 + 6], v[c8 * 8 + 7], make_float2(bB.z, bB.w));
+        *reinterpret_cast<uint4*>(tile + sw128_off(r, chunk0 + c8)) = o;
+    }
+}
+__device__ __forceinline__ void dbg_dump32(float* __restrict__ dst, const uint32_t (&v)[32], const float* __restrict__ bias) {
+    for (int c = 0; c < 32; ++c)
+        dst[c] = __bfloat162float(__float2bfloat16_rn(fmaxf(__uint_as_float(v[c]) + bias[c], 0.f)));
+}
+// running max over 32 columns with four independent FMNMX3 chains
+__device__ __forceinline__ void max32(const uint32_t (&v)[32], float (&m)[4]) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+        m[0] = max3(m[0], __uint_as_float(v[c + 0]), __uint_as_float(v[c + 1]));
+        m[1] = max3(m[1], __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+        m[2] = max3(m[2], __uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]));
+        m[3] = max3(m[3], __uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
+    }
+}
 
-// byte offset of 16-byte chunk `c` (8 bf16) of row `r` in a [rows x 64 bf16] 128B-swizzled K-major tile
-__host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c) { return r * 128u + (((c ^ (r & 7u)) & 7u) << 4); }
 
 // ---- the kernel ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsTc, 1)
@@ -258,24 +305,17 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             mbar_wait(bar(BAR_A3_EMPTY + buf), ((i >> 1) & 1) ^ 1);     // layer 3 of tile i-2 has released this buffer
             mbar_wait(bar(BAR_D1_FULL), i & 1);
             tc_fence_after();
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {                               // 2 x 32 channels
-                uint32_t v[32];
-                tc_ld32(lane_addr + kColD1 + g * 32, v);
+            {   // layer 1: 64 channels = two 32-column loads in flight, one wait
+                uint32_t v0[32], v1[32];
+                tc_ld32(lane_addr + kColD1, v0);
+                tc_ld32(lane_addr + kColD1 + 32, v1);
                 tc_wait_ld();
-                float f[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) f[c] = fmaxf(__uint_as_float(v[c]) + b1[g * 32 + c], 0.f);
-#pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    uint4 o;
-                    o.x = pack2(f[c8 * 8 + 0], f[c8 * 8 + 1]); o.y = pack2(f[c8 * 8 + 2], f[c8 * 8 + 3]);
-                    o.z = pack2(f[c8 * 8 + 4], f[c8 * 8 + 5]); o.w = pack2(f[c8 * 8 + 6], f[c8 * 8 + 7]);
-                    *reinterpret_cast<uint4*>(a3 + sw128_off(r, g * 4 + c8)) = o;
+                epi_store32(v0, b1, a3, r, 0);
+                epi_store32(v1, b1 + 32, a3, r, 4);
+                if (dbg_h1 && half == 0 && (int)r < valid) {
+                    dbg_dump32(dbg_h1 + (row0 + r) * 64, v0, b1);
+                    dbg_dump32(dbg_h1 + (row0 + r) * 64 + 32, v1, b1 + 32);
                 }
-                if (dbg_h1 && half == 0 && (int)r < valid)
-                    for (int c = 0; c < 32; ++c)
-                        dbg_h1[(row0 + r) * 64 + g * 32 + c] = __bfloat162float(__float2bfloat16_rn(f[c]));
             }
             fence_proxy_async();
             tc_fence_before();
@@ -285,24 +325,17 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             mbar_wait(bar(BAR_D2_FULL), i & 1);
             tc_fence_after();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {                               // 4 x 32 channels
-                uint32_t v[32];
-                tc_ld32(lane_addr + kColD2 + g * 32, v);
+            for (int kb = 0; kb < 2; ++kb) {                            // layer 2: 2 x 64 channels (= K halves of layer 3)
+                uint32_t v0[32], v1[32];
+                tc_ld32(lane_addr + kColD2 + kb * 64, v0);
+                tc_ld32(lane_addr + kColD2 + kb * 64 + 32, v1);
                 tc_wait_ld();
-                float f[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) f[c] = fmaxf(__uint_as_float(v[c]) + b2[g * 32 + c], 0.f);
-#pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    uint4 o;
-                    o.x = pack2(f[c8 * 8 + 0], f[c8 * 8 + 1]); o.y = pack2(f[c8 * 8 + 2], f[c8 * 8 + 3]);
-                    o.z = pack2(f[c8 * 8 + 4], f[c8 * 8 + 5]); o.w = pack2(f[c8 * 8 + 6], f[c8 * 8 + 7]);
-                    const uint32_t chunk = g * 4 + c8;                  // 0..15 over K = 128
-                    *reinterpret_cast<uint4*>(a3 + (chunk >> 3) * 16384 + sw128_off(r, chunk & 7)) = o;
+                epi_store32(v0, b2 + kb * 64, a3 + kb * 16384, r, 0);
+                epi_store32(v1, b2 + kb * 64 + 32, a3 + kb * 16384, r, 4);
+                if (dbg_h2 && half == 0 && (int)r < valid) {
+                    dbg_dump32(dbg_h2 + (row0 + r) * 128 + kb * 64, v0, b2 + kb * 64);
+                    dbg_dump32(dbg_h2 + (row0 + r) * 128 + kb * 64 + 32, v1, b2 + kb * 64 + 32);
                 }
-                if (dbg_h2 && half == 0 && (int)r < valid)
-                    for (int c = 0; c < 32; ++c)
-                        dbg_h2[(row0 + r) * 128 + g * 32 + c] = __bfloat162float(__float2bfloat16_rn(f[c]));
             }
             fence_proxy_async();
             tc_fence_before();
@@ -325,18 +358,23 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 mbar_wait(bar(BAR_D3_FULL + b), (q >> 1) & 1);
                 tc_fence_after();
                 float mm = m[cb];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t v[32];
-                    tc_ld32(lane_addr + kColD3 + b * 128 + g * 32, v);
+                {
+                    uint32_t v0[32], v1[32], v2[32], v3[32];           // all 128 point columns in flight, one wait
+                    const uint32_t a = lane_addr + kColD3 + b * 128;
+                    tc_ld32(a, v0); tc_ld32(a + 32, v1); tc_ld32(a + 64, v2); tc_ld32(a + 96, v3);
                     tc_wait_ld();
                     if (valid == kTile) {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) mm = fmaxf(mm, __uint_as_float(v[c]));
+                        float q[4] = {mm, -INFINITY, -INFINITY, -INFINITY};
+                        max32(v0, q); max32(v1, q); max32(v2, q); max32(v3, q);
+                        mm = fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3]));
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            if (g * 32 + c < valid) mm = fmaxf(mm, __uint_as_float(v[c]));
+                        for (int c = 0; c < 32; ++c) {
+                            if (c < valid) mm = fmaxf(mm, __uint_as_float(v0[c]));
+                            if (32 + c < valid) mm = fmaxf(mm, __uint_as_float(v1[c]));
+                            if (64 + c < valid) mm = fmaxf(mm, __uint_as_float(v2[c]));
+                            if (96 + c < valid) mm = fmaxf(mm, __uint_as_float(v3[c]));
+                        }
                     }
                 }
                 tc_fence_before();

@@ -16,8 +16,8 @@ __device__ __forceinline__ uint32_t f2key(float f) {
 // Selection by k passes of a block-wide arg-max over keys strictly below the previous winner.
 // key = (f2key(score) << 32) | (0xffffffff - index): unique per element, max = best.
 __global__ void __launch_bounds__(1024)
-zs_k_topk(const float* __restrict__ scores, int n, int k, int index_base, float* __restrict__ s_out,
-          int32_t* __restrict__ i_out) {
+zs_k_topk(const float* __restrict__ scores, int n, int k, int index_base, const int32_t* __restrict__ index_map,
+          float* __restrict__ s_out, int32_t* __restrict__ i_out) {
     __shared__ unsigned long long s_best[32];
     __shared__ unsigned long long s_prev;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -46,7 +46,7 @@ zs_k_topk(const float* __restrict__ scores, int n, int k, int index_base, float*
                 if (r < n) {
                     const int idx = (int)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
                     s_out[r] = scores[idx];
-                    i_out[r] = idx + index_base;
+                    i_out[r] = (index_map ? index_map[idx] : idx) + index_base;
                 } else {
                     s_out[r] = -INFINITY;
                     i_out[r] = -1;
@@ -60,13 +60,13 @@ zs_k_topk(const float* __restrict__ scores, int n, int k, int index_base, float*
 
 }  // namespace
 
-extern "C" int zs_topk(zs_ctx* ctx, const float* scores, int n, int k, int index_base, float* s_out,
-                       int32_t* i_out, void* stream) {
+extern "C" int zs_topk(zs_ctx* ctx, const float* scores, int n, int k, int index_base, const int32_t* index_map,
+                       float* s_out, int32_t* i_out, void* stream) {
     if (!ctx) return ZS_ERR_INVALID;
     if (n < 0 || k <= 0 || k > ZS_MAX_TOPK || !s_out || !i_out || (n > 0 && !scores))
         return zs_fail(ctx, ZS_ERR_INVALID, "zs_topk n %d k %d", n, k);
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
-    zs_k_topk<<<1, 1024, 0, (cudaStream_t)stream>>>(scores, n, k, index_base, s_out, i_out);
+    zs_k_topk<<<1, 1024, 0, (cudaStream_t)stream>>>(scores, n, k, index_base, index_map, s_out, i_out);
     ZS_LAUNCHED(ctx);
     return ZS_OK;
 }

@@ -201,10 +201,12 @@ class ZsContext:
                                   self._stream()), "zs_pool")
         return pooled
 
-    def head(self, wslot: int, pooled: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def head(self, wslot: int, pooled: torch.Tensor, tensor_cores: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(n,1024) pooled -> (n,) scores; tensor_cores=True: tf32 tcgen05 GEMMs, False: fp32 CUDA cores."""
         n = pooled.shape[0]
         scores = out if out is not None else torch.empty((n,), dtype=torch.float32, device=self.device)
-        self._ck(self.lib.zs_head(self.h, wslot, pooled.data_ptr(), n, scores.data_ptr(), self._stream()), "zs_head")
+        self._ck(self.lib.zs_head(self.h, wslot, pooled.data_ptr(), n, ZS_BF16 if tensor_cores else ZS_F32,
+                                  scores.data_ptr(), self._stream()), "zs_head")
         return scores
 
     def pool_debug(self, wslot: int, feat: torch.Tensor):
@@ -217,11 +219,13 @@ class ZsContext:
                                         h2.data_ptr(), self._stream()), "zs_pool_debug")
         return pooled, h1.view(n, N, 64), h2.view(n, N, 128)
 
-    def topk(self, scores: torch.Tensor, k: int, index_base: int = 0):
+    def topk(self, scores: torch.Tensor, k: int, index_base: int = 0, index_map: Optional[torch.Tensor] = None):
+        """Top-k by (score desc, index asc).  Returned index = index_map[i] (if given) + index_base."""
         s = torch.empty((k,), dtype=torch.float32, device=self.device)
         i = torch.empty((k,), dtype=torch.int32, device=self.device)
-        self._ck(self.lib.zs_topk(self.h, scores.data_ptr(), scores.shape[0], k, index_base, s.data_ptr(),
-                                  i.data_ptr(), self._stream()), "zs_topk")
+        self._ck(self.lib.zs_topk(self.h, scores.data_ptr() if scores.numel() else None, scores.shape[0], k, index_base,
+                                  index_map.data_ptr() if index_map is not None and index_map.numel() else None,
+                                  s.data_ptr(), i.data_ptr(), self._stream()), "zs_topk")
         return s, i
 
 

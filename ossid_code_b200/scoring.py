@@ -83,6 +83,7 @@ class FrameScorer:
         self.n_weights = len(weights)
         self._feat = None
         self._pooled = None
+        self._scores = None
         self._resident = None
         self.stage_events = None     # set to [] to record (stage, units, start_event, end_event) per launch group
 
@@ -137,39 +138,57 @@ class FrameScorer:
         """Featurise + score + top-k for the uploaded frame.  Returns (scores (n_obj,k), index (n_obj,k))
         tensors on the device; indices are global hypothesis indices per object, -1 = empty slot."""
         ctx, k = self.ctx, self.k
-        top_s, top_i = [], []
-        for r in self._resident:
-            poses12, N = r["poses12"], ctx.obj_npts[r["slot"]]
-            m = poses12.shape[0]
+        res = self._resident
+        tensor_cores = self.dtype == torch.bfloat16
+        # 1. free-space pre-filter per object (reads back one count per object when enabled)
+        keeps, n_keeps = [], []
+        for r in res:
             keep = None
-            if self.th < 100 and m > 0:
-                keep = ctx.filter(ctx.violations(r["slot"], poses12), N, self.th)
-            n_keep = m if keep is None else keep.shape[0]
-            scores = torch.empty((n_keep,), dtype=torch.float32, device=ctx.device)
+            if self.th < 100 and r["poses12"].shape[0] > 0:
+                keep = ctx.filter(ctx.violations(r["slot"], r["poses12"]), ctx.obj_npts[r["slot"]], self.th)
+            keeps.append(keep)
+            n_keeps.append(r["poses12"].shape[0] if keep is None else keep.shape[0])
+        # 2. objects laid out by weight slot so that the head runs once per scorer over a contiguous range
+        order = sorted(range(len(res)), key=lambda o: res[o]["wslot"])
+        offs, total = {}, 0
+        for o in order:
+            offs[o] = total
+            total += n_keeps[o]
+        if self._pooled is None or self._pooled.shape[0] < total:
+            self._pooled = torch.empty((max(total, 1), 1024), dtype=torch.float32, device=ctx.device)
+            self._scores = torch.empty((max(total, 1),), dtype=torch.float32, device=ctx.device)
+        # 3. features -> shared MLP + max-pool, chunked so that the feature buffer stays bounded
+        for o in order:
+            r, keep, n_keep = res[o], keeps[o], n_keeps[o]
+            poses12, N = r["poses12"], ctx.obj_npts[r["slot"]]
             for s in range(0, n_keep, self.chunk):
                 e = min(s + self.chunk, n_keep)
                 need = (e - s) * N * 8
                 if self._feat is None or self._feat.numel() < need or self._feat.dtype != self.dtype:
-                    self._feat = torch.empty((max(need, min(self.chunk, max(n_keep, 1)) * N * 8),),
-                                             dtype=self.dtype, device=ctx.device)
+                    self._feat = torch.empty((max(need, min(self.chunk, n_keep) * N * 8),), dtype=self.dtype,
+                                             device=ctx.device)
                 feat = self._feat[:need].view(e - s, N, 8)
-                if self._pooled is None or self._pooled.shape[0] < e - s:
-                    self._pooled = torch.empty((max(e - s, min(self.chunk, n_keep)), 1024), dtype=torch.float32,
-                                               device=ctx.device)
                 t = self._mark("features", (e - s) * N)
                 if keep is None:
                     ctx.features(r["slot"], poses12[s:e], n_keep=e - s, out=feat)
                 else:
                     ctx.features(r["slot"], poses12, keep_idx=keep[s:e], out=feat)
                 t = self._mark("pool", (e - s) * N, t)
-                pooled = ctx.pool(r["wslot"], feat, out=self._pooled[: e - s])
-                t = self._mark("head", e - s, t)
-                ctx.head(r["wslot"], pooled, out=scores[s:e])
+                ctx.pool(r["wslot"], feat, out=self._pooled[offs[o] + s: offs[o] + e])
                 self._mark(None, 0, t)
-            ts, ti = ctx.topk(scores, k, 0)
-            if keep is not None and n_keep > 0:      # position in the kept list -> local hypothesis index
-                ti = torch.where(ti >= 0, keep[ti.clamp(min=0).long()], ti)
-            ti = torch.where(ti >= 0, ti + r["lo"], ti)
+        # 4. head, one pass per scorer
+        for ws in sorted({res[o]["wslot"] for o in order}):
+            members = [o for o in order if res[o]["wslot"] == ws]
+            lo = offs[members[0]]
+            hi = offs[members[-1]] + n_keeps[members[-1]]
+            if hi > lo:
+                t = self._mark("head", hi - lo)
+                ctx.head(ws, self._pooled[lo:hi], tensor_cores, out=self._scores[lo:hi])
+                self._mark(None, 0, t)
+        # 5. per-object top-k; indices mapped back to global hypothesis indices inside the kernel
+        top_s, top_i = [], []
+        for o, r in enumerate(res):
+            ts, ti = ctx.topk(self._scores[offs[o]: offs[o] + n_keeps[o]], k, r["lo"], index_map=keeps[o])
             top_s.append(ts)
             top_i.append(ti)
         S, I = torch.stack(top_s), torch.stack(top_i)

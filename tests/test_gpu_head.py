@@ -1,0 +1,70 @@
+"""Tensor-core head (tf32 GEMMs fed by TMA) and the batched multi-object path, vs the oracle.  pytest -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import zephyr_oracle as zo
+from ossid_code_b200 import scoring, synthetic as syn, weights, zephyr_utils as glue
+from ossid_code_b200.engine import get_context
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return get_context(0)
+
+
+def _head_ref(pooled, w, tf32):
+    t = zo._tf32 if tf32 else (lambda x: x)
+    g = torch.relu(t(pooled) @ t(w["F1"]).T + w["c1"])
+    g = torch.relu(t(g) @ t(w["F2"]).T + w["c2"])
+    return (g @ w["F3"].T + w["c3"])[:, 0]
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 1000, 33000])
+def test_head_tensor_core_matches_oracle(ctx, n):
+    g = torch.Generator().manual_seed(n)
+    pooled = torch.relu(torch.randn(n, 1024, generator=g)) * 2.0          # pooled vectors are post-ReLU
+    w = weights.seeded_folded(4)
+    ctx.set_weights(2, w)
+    dev = pooled.to(ctx.device)
+    tc = ctx.head(2, dev, tensor_cores=True).cpu()
+    f32 = ctx.head(2, dev, tensor_cores=False).cpu()
+    ref32, reftf = _head_ref(pooled, w, False), _head_ref(pooled, w, True)
+    scale = float(ref32.abs().max())
+    assert float((f32 - ref32).abs().max()) <= 1e-4 * scale + 1e-6, "fp32 CUDA-core head"
+    e_tf, e_32 = float((tc - reftf).abs().max()), float((tc - ref32).abs().max())
+    print(f"n={n}: tf32 head vs tf32 oracle {e_tf:.3e}, vs fp32 oracle {e_32:.3e}, scale {scale:.2f}")
+    assert e_tf <= 1e-3 * scale + 1e-6, "tf32 tensor-core head vs tf32-emulating oracle"
+    assert e_32 <= 5e-3 * scale + 1e-6, "tf32 tensor-core head vs fp32 oracle"
+
+
+def test_topk_index_map(ctx):
+    s = torch.tensor([0.5, 3.0, 3.0, -1.0], device=ctx.device)
+    keep = torch.tensor([10, 20, 30, 40], dtype=torch.int32, device=ctx.device)
+    ts, ti = ctx.topk(s, 3, index_base=1000, index_map=keep)
+    assert ti.tolist() == [1020, 1030, 1010] and ts.tolist() == [3.0, 3.0, 0.5]
+
+
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_frame_scorer_batched_objects_two_scorers(ctx, precision, rtol):
+    """3 objects, 2 scorers keyed on object parity (online_learning.py:461-463), pre-filter on: per-object
+    top-k vs the oracle run object by object."""
+    sc = syn.make_scene(23, "lmo", n_obj=3, n_pts=300, n_hypo=500)
+    import cv2
+    img01 = cv2.GaussianBlur(sc["img"], (5, 5), 0) / 255.
+    meta = glue.K2meta(sc["cam_K"])
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    fs = scoring.FrameScorer(ws, device=0, precision=precision, inconst_ratio_th=10.0, k=5, chunk=170)
+    S, I = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=lambda o: o % 2)
+    for o, ob in enumerate(sc["objects"]):
+        f = zo.features(img01, sc["depth"], ob["pose_hypos"], meta, ob["model_points"], ob["model_colors"], ob["model_normals"])
+        keep = zo.violation_filter(f["viol"], 300, 10.0)
+        ref = zo.scorer(f["point_x"][keep], ws[o % 2])
+        es, ei = zo.topk(ref, 5)
+        tol = rtol * float(ref.abs().max()) + 1e-6
+        np.testing.assert_allclose(S[o, :len(es)], es.numpy(), rtol=0, atol=tol)
+        if len(es) > 1 and float(es[0] - es[1]) > 2 * tol:
+            assert int(I[o, 0]) == int(keep[ei[0]]), f"object {o}: top-1 differs"
+        assert set(I[o][I[o] >= 0].tolist()) <= set(keep.tolist())
