@@ -58,8 +58,18 @@ __device__ __forceinline__ void stage_cloud(const obj_view& o, float4*& sA, floa
 
 // ---------------------------------------------------------------------------------------
 // Features.  kBf16: feature dtype.  kSmem: model cloud staged in shared memory.
+// kAux: some side output (mask / uv / violation count) is requested.  Without side outputs the
+// mask bits are never materialised, so the rotated normal and its dot product (which then feed
+// only the 1e-4 cosine feature, not the bit-exact front-facing flag) may use FMAs.  Everything
+// that selects the gathered pixel or zeroes a feature stays on the exact path in both variants.
 // ---------------------------------------------------------------------------------------
-template <bool kBf16, bool kSmem>
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <bool kBf16, bool kSmem, bool kAux>
 __global__ void __launch_bounds__(kThreads)
 zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
               const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out,
@@ -89,26 +99,36 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
             if (act) {
                 const float4 a = kSmem ? sA[p] : __ldg(sA + p);
                 const float4 b = kSmem ? sB[p] : __ldg(sB + p);
-                const float vm = kSmem ? sV[p] : __ldg(sV + p);
                 float x, y, z, ur, vr;
                 zs_transform(T, a.x, a.y, a.z, x, y, z);
                 zs_project(cam, x, y, z, ur, vr);
                 const bool valid = (z > 0.f) && (z <= kFltMax) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
-                // R.n, same association as the points (no translation)
-                const float nx = xdot3(T.r[0], T.r[1], T.r[2], b.x, b.y, b.z);
-                const float ny = xdot3(T.r[4], T.r[5], T.r[6], b.x, b.y, b.z);
-                const float nz = xdot3(T.r[8], T.r[9], T.r[10], b.x, b.y, b.z);
-                const float dot = -xadd(xadd(xmul(x, nx), xmul(y, ny)), xmul(z, nz));
-                mk = dot > 0.f ? ZS_BIT_FRONT : 0;
+                float nx, ny, nz, dot;
+                if (kAux) {     // R.n and the dot product with the oracle's association: the front-facing bit is exact
+                    nx = xdot3(T.r[0], T.r[1], T.r[2], b.x, b.y, b.z);
+                    ny = xdot3(T.r[4], T.r[5], T.r[6], b.x, b.y, b.z);
+                    nz = xdot3(T.r[8], T.r[9], T.r[10], b.x, b.y, b.z);
+                    dot = -xadd(xadd(xmul(x, nx), xmul(y, ny)), xmul(z, nz));
+                    mk = dot > 0.f ? ZS_BIT_FRONT : 0;
+                }
                 if (valid) {
                     ui = (int)ur;
                     vi = (int)vr;
                     const float4 px = __ldg(frame + (size_t)vi * cam.W + ui);   // {d_obs, H, S, V}
+                    const float vm = kSmem ? sV[p] : __ldg(sV + p);
+                    if (!kAux) {
+                        nx = fmaf(T.r[0], b.x, fmaf(T.r[1], b.y, T.r[2] * b.z));
+                        ny = fmaf(T.r[4], b.x, fmaf(T.r[5], b.y, T.r[6] * b.z));
+                        nz = fmaf(T.r[8], b.x, fmaf(T.r[9], b.y, T.r[10] * b.z));
+                        dot = -fmaf(x, nx, fmaf(y, ny, z * nz));
+                    }
                     const bool vd = (px.x > 0.f) && (px.x <= kFltMax);
                     const float dD = vd ? xsub(px.x, z) : 0.f;
-                    mk |= ZS_BIT_VALID_PROJ | (vd ? ZS_BIT_VALID_DEPTH : 0);
-                    if (vd && dD > ZS_DEPTH_MARGIN) mk |= ZS_BIT_FREE_SPACE;
-                    if (vd && dD < -ZS_DEPTH_MARGIN) mk |= ZS_BIT_OCCLUDED;
+                    if (kAux) {
+                        mk |= ZS_BIT_VALID_PROJ | (vd ? ZS_BIT_VALID_DEPTH : 0);
+                        if (vd && dD > ZS_DEPTH_MARGIN) mk |= ZS_BIT_FREE_SPACE;
+                        if (vd && dD < -ZS_DEPTH_MARGIN) mk |= ZS_BIT_OCCLUDED;
+                    }
                     float dH = px.y - a.w;
                     dH = dH > 0.5f ? dH - 1.0f : dH;
                     dH = dH < -0.5f ? dH + 1.0f : dH;
@@ -119,12 +139,12 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
                     f4 = px.w - vm;
                     f5 = dD;
                     // cos of the angle between the viewing ray and the rotated normal
-                    // (python/ossid/datasets/ycbv_object.py:74); 1e-4 feature, so rsqrt is fine
-                    const float c = dot * rsqrtf(x * x + y * y + z * z) * rsqrtf(nx * nx + ny * ny + nz * nz);
+                    // (python/ossid/datasets/ycbv_object.py:74); a 1e-4 feature, so MUFU.RSQ is fine
+                    const float c = dot * rsqrt_fast(fmaf(x, x, fmaf(y, y, z * z))) * rsqrt_fast(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
                     f6 = (fabsf(c) <= kFltMax) ? c : 0.f;      // NaN / inf (degenerate pose) -> 0
                 }
             }
-            viol += __popc(__ballot_sync(0xffffffffu, (mk & ZS_BIT_FREE_SPACE) != 0));
+            if (kAux) viol += __popc(__ballot_sync(0xffffffffu, (mk & ZS_BIT_FREE_SPACE) != 0));
             if (act) {
                 if (kBf16) {
                     uint4 v;
@@ -136,11 +156,13 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
                     st_cs_f4(dst, make_float4(f0, f1, f2, f3));
                     st_cs_f4(dst + 1, make_float4(f4, f5, f6, 0.f));
                 }
-                if (mask_out) mask_out[row + p] = (uint8_t)mk;
-                if (uv_out) reinterpret_cast<int2*>(uv_out)[row + p] = make_int2(ui, vi);
+                if (kAux) {
+                    if (mask_out) mask_out[row + p] = (uint8_t)mk;
+                    if (uv_out) reinterpret_cast<int2*>(uv_out)[row + p] = make_int2(ui, vi);
+                }
             }
         }
-        if (viol_out && lane == 0) viol_out[hk] = viol;
+        if (kAux && viol_out && lane == 0) viol_out[hk] = viol;
     }
 }
 
@@ -330,19 +352,23 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t smem = (size_t)o.n_pts * 36;
     const bool in_smem = smem <= kCloudSmemMax;
-    const int ctas_per_sm = in_smem ? (int)max((size_t)1, min((size_t)4, (220 * 1024) / (smem + 1024))) : 4;
+    const bool aux = uv_out || mask_out || viol_out;
+    const size_t reg_limit = aux ? 4 : 5;       // 61 vs 46 registers per thread at 256 threads per CTA
+    const int ctas_per_sm = in_smem ? (int)max((size_t)1, min(reg_limit, (220 * 1024) / (smem + 1024))) : (int)reg_limit;
     const int grid = grid_for(ctx, n_keep, ctas_per_sm);
     cudaStream_t st = (cudaStream_t)stream;
     const float4* frame = ctx->frame.packed;
-#define ZS_LAUNCH_FEAT(BF, SM)                                                                          \
+#define ZS_LAUNCH_FEAT(BF, SM, AUX)                                                                     \
     do {                                                                                                \
-        rc = opt_in_smem(ctx, zs_k_features<BF, SM>, SM ? smem : 0);                                    \
+        rc = opt_in_smem(ctx, zs_k_features<BF, SM, AUX>, SM ? smem : 0);                               \
         if (rc) return rc;                                                                              \
-        zs_k_features<BF, SM><<<grid, kThreads, SM ? smem : 0, st>>>(o, cam, frame, poses, keep_idx,    \
-                                                                     n_keep, feat_out, uv_out, mask_out, viol_out); \
+        zs_k_features<BF, SM, AUX><<<grid, kThreads, SM ? smem : 0, st>>>(o, cam, frame, poses, keep_idx, \
+                                                                          n_keep, feat_out, uv_out, mask_out, viol_out); \
     } while (0)
-    if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_FEAT(true, true); else ZS_LAUNCH_FEAT(true, false); }
-    else                       { if (in_smem) ZS_LAUNCH_FEAT(false, true); else ZS_LAUNCH_FEAT(false, false); }
+#define ZS_LAUNCH_FEAT2(BF, SM) do { if (aux) ZS_LAUNCH_FEAT(BF, SM, true); else ZS_LAUNCH_FEAT(BF, SM, false); } while (0)
+    if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_FEAT2(true, true); else ZS_LAUNCH_FEAT2(true, false); }
+    else                       { if (in_smem) ZS_LAUNCH_FEAT2(false, true); else ZS_LAUNCH_FEAT2(false, false); }
+#undef ZS_LAUNCH_FEAT2
 #undef ZS_LAUNCH_FEAT
     ZS_LAUNCHED(ctx);
     return ZS_OK;

@@ -68,3 +68,27 @@ def test_frame_scorer_batched_objects_two_scorers(ctx, precision, rtol):
         if len(es) > 1 and float(es[0] - es[1]) > 2 * tol:
             assert int(I[o, 0]) == int(keep[ei[0]]), f"object {o}: top-1 differs"
         assert set(I[o][I[o] >= 0].tolist()) <= set(keep.tolist())
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-4), (torch.bfloat16, 2 ** -8)])
+@pytest.mark.parametrize("intr,n_pts,n_hypo", [("lmo", 1000, 400), ("hd", 4000, 60), ("tiny", 77, 50)])
+def test_features_without_side_outputs_match_oracle(ctx, dtype, rtol, intr, n_pts, n_hypo):
+    """The variant that runs when no mask/uv/violation output is requested (FrameScorer's hot path)."""
+    from ossid_code_b200.engine import poses_to_rt12
+    sc = syn.make_scene(41, intr, n_obj=1, n_pts=n_pts, n_hypo=n_hypo)
+    ob = sc["objects"][0]
+    import cv2
+    img01 = cv2.GaussianBlur(sc["img"], (5, 5), 0) / 255.
+    meta = glue.K2meta(sc["cam_K"])
+    ref = zo.features(img01, sc["depth"], ob["pose_hypos"], meta, ob["model_points"], ob["model_colors"], ob["model_normals"])
+    ctx.set_frame(img01, sc["depth"], meta)
+    ctx.set_object(0, ob["model_points"], ob["model_colors"], ob["model_normals"])
+    p12 = poses_to_rt12(ob["pose_hypos"], ctx.device)
+    hot, _, _, _ = ctx.features(0, p12, dtype=dtype)
+    aux, uv, mask, _ = ctx.features(0, p12, dtype=dtype, want_uv=True, want_mask=True)
+    assert torch.equal(uv.cpu(), ref["uv"]) and torch.equal(mask.cpu(), ref["mask"])
+    got = hot.float().cpu()
+    err = (got - ref["point_x"]).abs()
+    assert not bool((err > 1e-6 + rtol * ref["point_x"].abs()).any()), f"worst {float(err.max()):.3e}"
+    # zero pattern (invalid projections) must be identical to the exact variant
+    assert torch.equal(hot.float().abs().sum(-1) == 0, aux.float().abs().sum(-1) == 0)
