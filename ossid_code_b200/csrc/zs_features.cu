@@ -25,15 +25,32 @@ struct obj_view {
     int n_pts;
 };
 
+// bytes of shared memory taken by a staged model cloud, rounded so that what follows is 16-byte aligned
+__host__ __device__ __forceinline__ size_t cloud_smem(int n_pts) { return ((size_t)n_pts * 36 + 15) & ~(size_t)15; }
+
 __device__ __forceinline__ void st_cs_f4(float4* p, float4 v) {
-    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void st_cs_u4(uint4* p, uint4 v) {
-    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// fp32 features: a lane holds 32 contiguous bytes of its point, so a direct store would write two
+// half-filled 32-byte sectors per lane.  Stage the warp's 32 x 32 B through shared memory and write
+// two fully contiguous 512-byte warp stores instead.  `n_act` = points of this warp-iteration.
+__device__ __forceinline__ void store_f32_rows(float4* __restrict__ wbuf, int lane, float4* __restrict__ dst, int n_act,
+                                               float4 lo, float4 hi) {
+    wbuf[lane * 2] = lo;
+    wbuf[lane * 2 + 1] = hi;
+    __syncwarp();
+    const float4 c0 = wbuf[lane], c1 = wbuf[32 + lane];
+    if ((lane >> 1) < n_act) st_cs_f4(dst + lane, c0);
+    if (16 + (lane >> 1) < n_act) st_cs_f4(dst + 32 + lane, c1);
+    __syncwarp();
 }
 
 // Stage the model cloud into shared memory (or leave it in global when it does not fit).
@@ -42,7 +59,7 @@ __device__ __forceinline__ void stage_cloud(const obj_view& o, float4*& sA, floa
     if (kSmem) {
         sA = reinterpret_cast<float4*>(smem);
         sB = sA + o.n_pts;
-        sV = reinterpret_cast<float*>(sB + o.n_pts);
+        sV = reinterpret_cast<float*>(sB + o.n_pts);   // the per-warp fp32 store staging follows the cloud (see cloud_smem)
         for (int i = threadIdx.x; i < o.n_pts; i += blockDim.x) {
             sA[i] = __ldg(o.pA + i);
             sB[i] = __ldg(o.pB + i);
@@ -84,15 +101,25 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
     const int n_warps = gridDim.x * kWarpsPerCta;
     const int N = o.n_pts;
     const float fW = (float)cam.W, fH = (float)cam.H;
+    float4* wbuf = reinterpret_cast<float4*>(smem + (kSmem ? cloud_smem(N) : 0)) + (threadIdx.x >> 5) * 64;
 
-    for (int hk = warp; hk < n_keep; hk += n_warps) {
+    // Work unit: with side outputs a warp owns a whole hypothesis (its violation count is a warp-local
+    // sum); without them a unit is a 256-point chunk of a hypothesis, which keeps the last wave of a
+    // 10k-hypothesis launch short (units / resident warps ~ 7 instead of ~ 2).
+    constexpr int kChunk = 256;
+    const int n_chunks = kAux ? 1 : (N + kChunk - 1) / kChunk;
+    const long long n_units = (long long)n_keep * n_chunks;
+    for (long long u = warp; u < n_units; u += n_warps) {
+        const int hk = kAux ? (int)u : (int)(u / n_chunks);
+        const int p_begin = kAux ? 0 : (int)(u - (long long)hk * n_chunks) * kChunk;
+        const int p_end = kAux ? N : min(N, p_begin + kChunk);
         const int h = keep_idx ? __ldg(keep_idx + hk) : hk;
         const zs_pose T = zs_load_pose(poses, h);
         const size_t row = (size_t)hk * N;
         int viol = 0;
-        for (int p0 = 0; p0 < N; p0 += 32) {
+        for (int p0 = p_begin; p0 < p_end; p0 += 32) {
             const int p = p0 + lane;
-            const bool act = p < N;
+            const bool act = p < p_end;
             uint32_t mk = 0;
             float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f, f5 = 0.f, f6 = 0.f;
             int ui = 0, vi = 0;
@@ -145,17 +172,18 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
                 }
             }
             if (kAux) viol += __popc(__ballot_sync(0xffffffffu, (mk & ZS_BIT_FREE_SPACE) != 0));
-            if (act) {
-                if (kBf16) {
+            if (kBf16) {
+                if (act) {
                     uint4 v;
                     v.x = pack_bf16x2(f0, f1); v.y = pack_bf16x2(f2, f3);
                     v.z = pack_bf16x2(f4, f5); v.w = pack_bf16x2(f6, 0.f);
                     st_cs_u4(reinterpret_cast<uint4*>(feat_out) + row + p, v);
-                } else {
-                    float4* dst = reinterpret_cast<float4*>(feat_out) + (row + p) * 2;
-                    st_cs_f4(dst, make_float4(f0, f1, f2, f3));
-                    st_cs_f4(dst + 1, make_float4(f4, f5, f6, 0.f));
                 }
+            } else {
+                store_f32_rows(wbuf, lane, reinterpret_cast<float4*>(feat_out) + (row + p0) * 2, p_end - p0,
+                               make_float4(f0, f1, f2, f3), make_float4(f4, f5, f6, 0.f));
+            }
+            if (act) {
                 if (kAux) {
                     if (mask_out) mask_out[row + p] = (uint8_t)mk;
                     if (uv_out) reinterpret_cast<int2*>(uv_out)[row + p] = make_int2(ui, vi);
@@ -163,6 +191,103 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
             }
         }
         if (kAux && viol_out && lane == 0) viol_out[hk] = viol;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Hot variant: features only (no mask / uv / violation outputs).  Work unit = 256-point chunk of a
+// hypothesis (short last wave); each lane carries kIlp points per iteration so that kIlp frame
+// gathers are in flight per warp (the kernel is otherwise bound by the latency of that gather).
+// Arithmetic is the same as zs_k_features<.,.,false>.
+// ---------------------------------------------------------------------------------------
+template <bool kBf16, bool kSmem>
+__global__ void __launch_bounds__(kThreads, 4)
+zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
+                  const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out) {
+    extern __shared__ __align__(16) char smem[];
+    float4 *sA, *sB;
+    float* sV;
+    stage_cloud<kSmem>(o, sA, sB, sV, smem);
+    constexpr int kIlp = 2, kChunk = 256;
+    float4* wbuf = reinterpret_cast<float4*>(smem + (kSmem ? cloud_smem(o.n_pts) : 0)) + (threadIdx.x >> 5) * 64;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerCta;
+    const int N = o.n_pts;
+    const float fW = (float)cam.W, fH = (float)cam.H;
+    const int n_chunks = (N + kChunk - 1) / kChunk;
+    const long long n_units = (long long)n_keep * n_chunks;
+    for (long long u = warp; u < n_units; u += n_warps) {
+        const int hk = (int)(u / n_chunks);
+        const int p_begin = (int)(u - (long long)hk * n_chunks) * kChunk;
+        const int p_end = min(N, p_begin + kChunk);
+        const int h = keep_idx ? __ldg(keep_idx + hk) : hk;
+        const zs_pose T = zs_load_pose(poses, h);
+        const size_t row = (size_t)hk * N;
+        for (int p0 = p_begin; p0 < p_end; p0 += 32 * kIlp) {
+            float4 a[kIlp], b[kIlp], px[kIlp];
+            float x[kIlp], y[kIlp], z[kIlp];
+            int ui[kIlp], vi[kIlp];
+            bool valid[kIlp];
+#pragma unroll
+            for (int j = 0; j < kIlp; ++j) {                 // phase 1: exact projection, issue the gather
+                const int p = p0 + j * 32 + lane;
+                valid[j] = false;
+                ui[j] = vi[j] = 0;
+                px[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p < p_end) {
+                    a[j] = kSmem ? sA[p] : __ldg(sA + p);
+                    float ur, vr;
+                    zs_transform(T, a[j].x, a[j].y, a[j].z, x[j], y[j], z[j]);
+                    zs_project(cam, x[j], y[j], z[j], ur, vr);
+                    valid[j] = (z[j] > 0.f) && (z[j] <= kFltMax) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
+                    if (valid[j]) {
+                        ui[j] = (int)ur;
+                        vi[j] = (int)vr;
+                        px[j] = __ldg(frame + (size_t)vi[j] * cam.W + ui[j]);   // {d_obs, H, S, V}
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kIlp; ++j) {                 // phase 2: residual features, store
+                const int p = p0 + j * 32 + lane;
+                const int n_act = p_end - (p0 + j * 32);      // warp-uniform
+                if (n_act <= 0) continue;
+                float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f, f5 = 0.f, f6 = 0.f;
+                if (valid[j]) {
+                    b[j] = kSmem ? sB[p] : __ldg(sB + p);
+                    const float vm = kSmem ? sV[p] : __ldg(sV + p);
+                    const float nx = fmaf(T.r[0], b[j].x, fmaf(T.r[1], b[j].y, T.r[2] * b[j].z));
+                    const float ny = fmaf(T.r[4], b[j].x, fmaf(T.r[5], b[j].y, T.r[6] * b[j].z));
+                    const float nz = fmaf(T.r[8], b[j].x, fmaf(T.r[9], b[j].y, T.r[10] * b[j].z));
+                    const float dot = -fmaf(x[j], nx, fmaf(y[j], ny, z[j] * nz));
+                    const bool vd = (px[j].x > 0.f) && (px[j].x <= kFltMax);
+                    float dH = px[j].y - a[j].w;
+                    dH = dH > 0.5f ? dH - 1.0f : dH;
+                    dH = dH < -0.5f ? dH + 1.0f : dH;
+                    f0 = ((float)ui[j] - cam.cx) * cam.inv_fx;
+                    f1 = ((float)vi[j] - cam.cy) * cam.inv_fy;
+                    f2 = dH;
+                    f3 = px[j].z - b[j].w;
+                    f4 = px[j].w - vm;
+                    f5 = vd ? xsub(px[j].x, z[j]) : 0.f;
+                    const float c = dot * rsqrt_fast(fmaf(x[j], x[j], fmaf(y[j], y[j], z[j] * z[j]))) *
+                                    rsqrt_fast(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+                    f6 = (fabsf(c) <= kFltMax) ? c : 0.f;
+                }
+                if (kBf16) {
+                    if (p < p_end) {
+                        uint4 v;
+                        v.x = pack_bf16x2(f0, f1); v.y = pack_bf16x2(f2, f3);
+                        v.z = pack_bf16x2(f4, f5); v.w = pack_bf16x2(f6, 0.f);
+                        st_cs_u4(reinterpret_cast<uint4*>(feat_out) + row + p, v);
+                    }
+                } else {
+                    store_f32_rows(wbuf, lane, reinterpret_cast<float4*>(feat_out) + (row + p0 + j * 32) * 2, n_act,
+                                   make_float4(f0, f1, f2, f3), make_float4(f4, f5, f6, 0.f));
+                }
+            }
+        }
     }
 }
 
@@ -350,25 +475,32 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
     if (!feat_out || ((uintptr_t)feat_out & 15) || (uv_out && ((uintptr_t)uv_out & 7)))
         return zs_fail(ctx, ZS_ERR_INVALID, "feat_out must be 16-byte aligned (uv_out 8)");
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t smem = (size_t)o.n_pts * 36;
-    const bool in_smem = smem <= kCloudSmemMax;
+    const size_t stage = feat_dtype == ZS_F32 ? (size_t)kWarpsPerCta * 1024 : 0;   // fp32 store staging, 1 KB per warp
+    const bool in_smem = cloud_smem(o.n_pts) <= kCloudSmemMax;
+    const size_t smem = (in_smem ? cloud_smem(o.n_pts) : 0) + stage;
     const bool aux = uv_out || mask_out || viol_out;
-    const size_t reg_limit = aux ? 4 : 5;       // 61 vs 46 registers per thread at 256 threads per CTA
+    const size_t reg_limit = 4;                 // <= 64 registers per thread at 256 threads per CTA
     const int ctas_per_sm = in_smem ? (int)max((size_t)1, min(reg_limit, (220 * 1024) / (smem + 1024))) : (int)reg_limit;
-    const int grid = grid_for(ctx, n_keep, ctas_per_sm);
+    const long long units = aux ? n_keep : (long long)n_keep * ((o.n_pts + 255) / 256);
+    const int grid = grid_for(ctx, (int)min(units, (long long)1 << 30), ctas_per_sm);
     cudaStream_t st = (cudaStream_t)stream;
     const float4* frame = ctx->frame.packed;
-#define ZS_LAUNCH_FEAT(BF, SM, AUX)                                                                     \
+#define ZS_LAUNCH_FEAT(BF, SM)                                                                          \
     do {                                                                                                \
-        rc = opt_in_smem(ctx, zs_k_features<BF, SM, AUX>, SM ? smem : 0);                               \
-        if (rc) return rc;                                                                              \
-        zs_k_features<BF, SM, AUX><<<grid, kThreads, SM ? smem : 0, st>>>(o, cam, frame, poses, keep_idx, \
-                                                                          n_keep, feat_out, uv_out, mask_out, viol_out); \
+        if (aux) {                                                                                      \
+            rc = opt_in_smem(ctx, zs_k_features<BF, SM, true>, smem);                          \
+            if (rc) return rc;                                                                          \
+            zs_k_features<BF, SM, true><<<grid, kThreads, smem, st>>>(                         \
+                o, cam, frame, poses, keep_idx, n_keep, feat_out, uv_out, mask_out, viol_out);          \
+        } else {                                                                                        \
+            rc = opt_in_smem(ctx, zs_k_features_hot<BF, SM>, smem);                            \
+            if (rc) return rc;                                                                          \
+            zs_k_features_hot<BF, SM><<<grid, kThreads, smem, st>>>(o, cam, frame, poses,      \
+                                                                              keep_idx, n_keep, feat_out); \
+        }                                                                                               \
     } while (0)
-#define ZS_LAUNCH_FEAT2(BF, SM) do { if (aux) ZS_LAUNCH_FEAT(BF, SM, true); else ZS_LAUNCH_FEAT(BF, SM, false); } while (0)
-    if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_FEAT2(true, true); else ZS_LAUNCH_FEAT2(true, false); }
-    else                       { if (in_smem) ZS_LAUNCH_FEAT2(false, true); else ZS_LAUNCH_FEAT2(false, false); }
-#undef ZS_LAUNCH_FEAT2
+    if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_FEAT(true, true); else ZS_LAUNCH_FEAT(true, false); }
+    else                       { if (in_smem) ZS_LAUNCH_FEAT(false, true); else ZS_LAUNCH_FEAT(false, false); }
 #undef ZS_LAUNCH_FEAT
     ZS_LAUNCHED(ctx);
     return ZS_OK;

@@ -24,6 +24,28 @@ def shard_range(n: int, rank: int, world: int):
     return lo, min(lo + per, n)
 
 
+def spatial_order(points) -> np.ndarray:
+    """Permutation that sorts model points along a 3-D Morton (Z-order) curve.
+
+    The scorer is invariant to the order of a hypothesis' points (shared MLP + max-pool), so the hot
+    path uploads the cloud in this order: the 32 points a warp projects together then land on a
+    compact image patch and their frame gathers share 128-byte lines instead of touching 32.
+    """
+    p = np.asarray(points, dtype=np.float64)
+    lo, hi = p.min(axis=0), p.max(axis=0)
+    q = ((p - lo) / np.where(hi > lo, hi - lo, 1.0) * 1023.0).astype(np.uint64)
+
+    def spread(v):                                   # 10 bits -> every third bit
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    return np.argsort(code, kind="stable")
+
+
 def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k: int):
     """Merge candidate lists (..., C) -> (..., k) by (score desc, index asc); empty slots are (-inf, -1).
 
@@ -70,7 +92,7 @@ class FrameScorer:
 
     def __init__(self, weights: Sequence[dict], device: Optional[int] = None, precision: str = "bf16",
                  inconst_ratio_th: float = 100.0, k: int = 8, chunk: int = 32768, group=None,
-                 ctx: Optional[ZsContext] = None):
+                 ctx: Optional[ZsContext] = None, reorder_points: bool = True):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         if device is None:
@@ -81,6 +103,7 @@ class FrameScorer:
         for slot, w in enumerate(weights):
             self.ctx.set_weights(slot, w)
         self.n_weights = len(weights)
+        self.reorder_points = reorder_points
         self._feat = None
         self._pooled = None
         self._scores = None
@@ -125,7 +148,14 @@ class FrameScorer:
         res = []
         for o, ob in enumerate(objects):
             slot = o % 64
-            ctx.set_object(slot, ob["model_points"], ob["model_colors"], ob["model_normals"])
+            pts, cols, nrms = (torch.as_tensor(ob[key]) for key in ("model_points", "model_colors", "model_normals"))
+            if self.reorder_points:
+                perm = ob.get("_zs_order")
+                if perm is None:                      # cached on the object dict: clouds are reused frame after frame
+                    perm = torch.from_numpy(spatial_order(pts.cpu().numpy()))
+                    ob["_zs_order"] = perm
+                pts, cols, nrms = pts[perm], cols[perm], nrms[perm]
+            ctx.set_object(slot, pts, cols, nrms)
             M = len(ob["pose_hypos"])
             lo, hi = shard_range(M, rank, world)
             poses12 = poses_to_rt12(torch.as_tensor(ob["pose_hypos"])[lo:hi], ctx.device)
