@@ -66,41 +66,69 @@ def make_workload(name, n_gpus, seed=1):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples while the timed region runs (B200_PROFILING.md)."""
+    """nvidia-smi clock / throttle-reason samples while the timed region runs (B200_PROFILING.md).
+
+    Started before the warm-up (nvidia-smi needs a few hundred ms to produce its first line); samples are
+    time-stamped on arrival and only those inside [mark_start, mark_stop] are summarised.
+    """
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.proc = gpu_index, None
+        self.idx, self.proc, self.rows, self.t0, self.t1 = gpu_index, None, [], None, None
+
+    def _reader(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line))
 
     def start(self):
+        import threading
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True, bufsize=1)
         except OSError:
             self.proc = None
+            return
+        self.thread = threading.Thread(target=self._reader, daemon=True)
+        self.thread.start()
+        t_end = time.perf_counter() + 5.0
+        while not self.rows and time.perf_counter() < t_end:      # wait for the first sample
+            time.sleep(0.02)
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_stop(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.12)
         self.proc.terminate()
-        out, _ = self.proc.communicate(timeout=10)
-        sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
+        try:
+            self.proc.wait(timeout=10)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        inside = [l for (t, l) in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.06]
+        scope = "timed region"
+        if len(inside) < 2:                                        # very short run: fall back to everything under load
+            inside, scope = [l for (_, l) in self.rows], "warm-up + timed region"
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in inside:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def cpu_reference_run(sample, n_repeat):
@@ -156,7 +184,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -207,12 +235,13 @@ def main():
 
     # ---- device-resident arm: `value` ------------------------------------------------------------
     fs.upload(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of)
-    for _ in range(args.warmup):
-        S, I = fs.run_resident()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        S, I = fs.run_resident()
+    barrier()
+    sampler.mark_start()
     fs.stage_events = []
     l0 = fs.ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -221,6 +250,7 @@ def main():
         S, I = fs.run_resident()
     e1.record()
     barrier()
+    sampler.mark_stop()
     launches = fs.ctx.launches - l0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
@@ -270,6 +300,29 @@ def main():
                                      "ms_in_timed_region": st["ms"], "share_of_step": st["ms"] / (ms_step * args.steps)}
     if "head" in stages:
         roof["head_share_of_step"] = stages["head"]["ms"] / (ms_step * args.steps)
+    # The same feature kernel writing fp32 features (the 1e-4 parity configuration), timed alone on this
+    # rank's hypotheses of object 0 replicated to >= 32768 (output 1 GB, far beyond L2): context for the
+    # in-step bf16 figure above, which moves half the bytes per point and is issue-bound instead.
+    r0 = fs._resident[0]
+    reps = max(1, -(-32768 // max(r0["poses12"].shape[0], 1)))
+    p_big = r0["poses12"].repeat(reps, 1)[:32768].contiguous()
+    buf = torch.empty((p_big.shape[0], n_pts, 8), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        fs.ctx.features(r0["slot"], p_big, out=buf)
+    torch.cuda.synchronize(dev)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(5):
+        fs.ctx.features(r0["slot"], p_big, out=buf)
+    k1.record()
+    torch.cuda.synchronize(dev)
+    k_ms = k0.elapsed_time(k1) / 5
+    k_bytes = p_big.shape[0] * (48 + n_pts * 32)
+    roof["roofline_features_fp32"] = {"kernel": "zs_features, fp32 features, standalone launch of 32768 hypotheses",
+                                      "bound": "hbm", "achieved": k_bytes / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm"],
+                                      "unit": "GB/s", "frac": k_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm"],
+                                      "ms_per_launch": k_ms, "hypotheses_per_s": p_big.shape[0] / (k_ms * 1e-3)}
+    del buf
 
     line = {
         "metric": "hypotheses_scored_per_sec", "value": value, "unit": "hypotheses/s", "n_gpus": world,
