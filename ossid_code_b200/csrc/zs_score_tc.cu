@@ -20,10 +20,11 @@
 // Warp roles (320 threads): warps 0-3 front epilogues (D1 -> H1, D2 -> H2), warps 4-7 max-pool
 // epilogue (D3), warp 8 bulk-copy producer (weights once, then feature tiles, 3 stages), warp 9
 // TMEM allocator + single-thread MMA issuer.  Front of tile i+1 overlaps layer 3 of tile i; D3 is
-// double-buffered in TMEM (cols: D1 0-63, D2 64-191, D3 192-319 / 320-447).  H1 aliases the H2
+// triple-buffered in TMEM (cols: D1 0-63 inside D2 0-127, D3 128-255 / 256-383 / 384-511).  H1 aliases the H2
 // buffer that the same tile's epilogue 2 overwrites afterwards, which is what makes two H2
 // buffers + the resident weights fit in 227 KB.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "zs_common.cuh"
 
@@ -51,11 +52,15 @@ static_assert(kSmAlloc <= 232448, "exceeds 227 KB of shared memory per CTA");
 // barrier slots
 enum : int {
     BAR_W_FULL = 0, BAR_X_FULL = 1 /*3*/, BAR_X_EMPTY = 4 /*3*/, BAR_D1_FULL = 7, BAR_A2_FULL = 8, BAR_D2_FULL = 9,
-    BAR_A3_FULL = 10 /*2*/, BAR_A3_EMPTY = 12 /*2*/, BAR_D3_FULL = 14 /*2*/, BAR_D3_EMPTY = 16 /*2*/, BAR_COUNT = 18
+    BAR_A3_FULL = 10 /*2*/, BAR_A3_EMPTY = 12 /*2*/, BAR_D3_FULL = 14 /*3*/, BAR_D3_EMPTY = 17 /*3*/, BAR_COUNT = 20
 };
 
 // TMEM columns
-constexpr uint32_t kColD1 = 0, kColD2 = 64, kColD3 = 192;
+// D1 (64 cols) lives inside D2's 128 columns: D1 is dead once epilogue 1 has signalled A2_FULL, which the
+// issuer waits for before layer 2 overwrites the range, and layer 1 of the next tile is only issued after
+// A3_FULL of this tile (epilogue 2 has drained D2).  That leaves room for THREE layer-3 accumulators.
+constexpr uint32_t kColD1 = 0, kColD2 = 0, kColD3 = 128;
+constexpr int kD3Bufs = 3;
 constexpr uint32_t kTmemCols = 512;
 
 // global image of the bf16 operands (bytes): W3 half 0, W3 half 1, W2, W1
@@ -186,7 +191,7 @@ __device__ __forceinline__ void max32(const uint32_t (&v)[32], float (&m)[4]) {
 __global__ void __launch_bounds__(kThreadsTc, 1)
 zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t* __restrict__ wimg,
             const float* __restrict__ wf32, float* __restrict__ pooled, float* __restrict__ dbg_h1,
-            float* __restrict__ dbg_h2) {
+            float* __restrict__ dbg_h2, int experiment) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
@@ -204,10 +209,8 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
         mbar_init(bar(BAR_W_FULL), 1);
         for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_X_FULL + s), 1); mbar_init(bar(BAR_X_EMPTY + s), 1); }
         mbar_init(bar(BAR_D1_FULL), 1); mbar_init(bar(BAR_A2_FULL), 1); mbar_init(bar(BAR_D2_FULL), 1);
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bar(BAR_A3_FULL + b), 1); mbar_init(bar(BAR_A3_EMPTY + b), 1);
-            mbar_init(bar(BAR_D3_FULL + b), 1); mbar_init(bar(BAR_D3_EMPTY + b), 1);
-        }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar(BAR_A3_FULL + b), 1); mbar_init(bar(BAR_A3_EMPTY + b), 1); }
+        for (int b = 0; b < kD3Bufs; ++b) { mbar_init(bar(BAR_D3_FULL + b), 1); mbar_init(bar(BAR_D3_EMPTY + b), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // zero the feature stages and the zero block (stale bytes must be finite), stage the small biases
@@ -250,9 +253,8 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             mbar_wait(bar(BAR_W_FULL), 0);
             tc_fence_after();
             auto issue_l3 = [&](int it, int cb) {           // layer 3, channel block cb of tile `it`
-                const int q = it * 4 + cb, b = cb & 1, buf = it & 1;
-                if (cb == 0) { mbar_wait(bar(BAR_A3_FULL + buf), (it >> 1) & 1); }
-                mbar_wait(bar(BAR_D3_EMPTY + b), ((q >> 1) & 1) ^ 1);
+                const int q = it * 4 + cb, b = q % kD3Bufs, buf = it & 1;   // A3_FULL of tile `it` was awaited by the caller
+                if (!experiment) mbar_wait(bar(BAR_D3_EMPTY + b), ((q / kD3Bufs) & 1) ^ 1);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -265,6 +267,8 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 if (cb == 3) tc_commit(bar(BAR_A3_EMPTY + buf));
             };
             for (int i = 0; i <= total; ++i) {
+                // H2 of tile i-1 is ready and D2 (which D1 aliases) has been drained by epilogue 2
+                if (i >= 1 && !experiment) mbar_wait(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1);
                 if (i < total) {
                     const int s = i % kStages;
                     mbar_wait(bar(BAR_X_FULL + s), (i / kStages) & 1);
@@ -276,9 +280,9 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                     tc_commit(bar(BAR_X_EMPTY + s));
                     tc_commit(bar(BAR_D1_FULL));
                 }
-                if (i >= 1) { issue_l3(i - 1, 0); issue_l3(i - 1, 1); }
+                if (i >= 1) { issue_l3(i - 1, 0); }
                 if (i < total) {
-                    mbar_wait(bar(BAR_A2_FULL), i & 1);
+                    if (!experiment) mbar_wait(bar(BAR_A2_FULL), i & 1);
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
@@ -288,9 +292,11 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                     }
                     tc_commit(bar(BAR_D2_FULL));
                 }
-                if (i >= 1) { issue_l3(i - 1, 2); issue_l3(i - 1, 3); }
+                if (i >= 1) { issue_l3(i - 1, 1); issue_l3(i - 1, 2); issue_l3(i - 1, 3); }
             }
         }
+    } else if (experiment) {
+        // timing experiment: tensor pipe + bulk copies only, epilogue warps idle
     } else if (warp < 4) {
         // ===== front epilogues: D1 -> H1 (bf16, swizzled), D2 -> H2 ================================
         const uint32_t r = (uint32_t)tid;                               // TMEM lane = point row of the tile
@@ -354,8 +360,8 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             const int valid = min(kTile, N - tt * kTile);
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
-                const int q = i * 4 + cb, b = cb & 1;
-                mbar_wait(bar(BAR_D3_FULL + b), (q >> 1) & 1);
+                const int q = i * 4 + cb, b = q % kD3Bufs;
+                mbar_wait(bar(BAR_D3_FULL + b), (q / kD3Bufs) & 1);
                 tc_fence_after();
                 float mm = m[cb];
                 {
@@ -447,7 +453,7 @@ static int launch_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, in
     int grid = ctx->sm_count & ~1;                 // CTA pairs
     if (grid > 2 * n) grid = 2 * n;
     zs_k_mlp_tc<<<grid, kThreadsTc, kSmAlloc, st>>>(feat, n, n_pts, reinterpret_cast<const uint8_t*>(w.bf16), w.f32,
-                                                     pooled, dbg_h1, dbg_h2);
+                                                     pooled, dbg_h1, dbg_h2, getenv("ZS_TC_EXPERIMENT") ? atoi(getenv("ZS_TC_EXPERIMENT")) : 0);
     ZS_LAUNCHED(ctx);
     return ZS_OK;
 }
