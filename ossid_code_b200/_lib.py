@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzs.so")
+LIB_PATH = os.environ.get("ZS_LIB") or os.path.join(HERE, "libzs.so")   # ZS_LIB: A/B builds in tools/
 
 ZS_F32, ZS_BF16 = 0, 1
 ZS_MAX_TOPK = 64

@@ -24,7 +24,6 @@
 // buffer that the same tile's epilogue 2 overwrites afterwards, which is what makes two H2
 // buffers + the resident weights fit in 227 KB.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "zs_common.cuh"
 
@@ -191,7 +190,7 @@ __device__ __forceinline__ void max32(const uint32_t (&v)[32], float (&m)[4]) {
 __global__ void __launch_bounds__(kThreadsTc, 1)
 zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t* __restrict__ wimg,
             const float* __restrict__ wf32, float* __restrict__ pooled, float* __restrict__ dbg_h1,
-            float* __restrict__ dbg_h2, int experiment) {
+            float* __restrict__ dbg_h2) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
@@ -254,7 +253,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             tc_fence_after();
             auto issue_l3 = [&](int it, int cb) {           // layer 3, channel block cb of tile `it`
                 const int q = it * 4 + cb, b = q % kD3Bufs, buf = it & 1;   // A3_FULL of tile `it` was awaited by the caller
-                if (!experiment) mbar_wait(bar(BAR_D3_EMPTY + b), ((q / kD3Bufs) & 1) ^ 1);
+                mbar_wait(bar(BAR_D3_EMPTY + b), ((q / kD3Bufs) & 1) ^ 1);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -268,7 +267,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             };
             for (int i = 0; i <= total; ++i) {
                 // H2 of tile i-1 is ready and D2 (which D1 aliases) has been drained by epilogue 2
-                if (i >= 1 && !experiment) mbar_wait(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1);
+                if (i >= 1) mbar_wait(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1);
                 if (i < total) {
                     const int s = i % kStages;
                     mbar_wait(bar(BAR_X_FULL + s), (i / kStages) & 1);
@@ -282,7 +281,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 }
                 if (i >= 1) { issue_l3(i - 1, 0); }
                 if (i < total) {
-                    if (!experiment) mbar_wait(bar(BAR_A2_FULL), i & 1);
+                    mbar_wait(bar(BAR_A2_FULL), i & 1);
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
@@ -295,8 +294,6 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 if (i >= 1) { issue_l3(i - 1, 1); issue_l3(i - 1, 2); issue_l3(i - 1, 3); }
             }
         }
-    } else if (experiment) {
-        // timing experiment: tensor pipe + bulk copies only, epilogue warps idle
     } else if (warp < 4) {
         // ===== front epilogues: D1 -> H1 (bf16, swizzled), D2 -> H2 ================================
         const uint32_t r = (uint32_t)tid;                               // TMEM lane = point row of the tile
@@ -453,7 +450,7 @@ static int launch_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, in
     int grid = ctx->sm_count & ~1;                 // CTA pairs
     if (grid > 2 * n) grid = 2 * n;
     zs_k_mlp_tc<<<grid, kThreadsTc, kSmAlloc, st>>>(feat, n, n_pts, reinterpret_cast<const uint8_t*>(w.bf16), w.f32,
-                                                     pooled, dbg_h1, dbg_h2, getenv("ZS_TC_EXPERIMENT") ? atoi(getenv("ZS_TC_EXPERIMENT")) : 0);
+                                                     pooled, dbg_h1, dbg_h2);
     ZS_LAUNCHED(ctx);
     return ZS_OK;
 }
