@@ -14,8 +14,9 @@
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 8;               // default CTA: 8 warps; big model clouds use up to 32 (see cta_shape)
 constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kMaxThreads = 1024;
 constexpr float kFltMax = 3.402823466e38f;   // 0 < z <= FLT_MAX, i.e. finite (oracle: z < inf)
 
 struct obj_view {
@@ -87,7 +88,7 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 }
 
 template <bool kBf16, bool kSmem, bool kAux>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
               const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out,
               int32_t* __restrict__ uv_out, uint8_t* __restrict__ mask_out, int32_t* __restrict__ viol_out) {
@@ -97,8 +98,9 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
     stage_cloud<kSmem>(o, sA, sB, sV, smem);
 
     const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    const int n_warps = gridDim.x * kWarpsPerCta;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * warps_per_cta;
     const int N = o.n_pts;
     const float fW = (float)cam.W, fH = (float)cam.H;
     float4* wbuf = reinterpret_cast<float4*>(smem + (kSmem ? cloud_smem(N) : 0)) + (threadIdx.x >> 5) * 64;
@@ -201,7 +203,7 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
 // Arithmetic is the same as zs_k_features<.,.,false>.
 // ---------------------------------------------------------------------------------------
 template <bool kBf16, bool kSmem>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
                   const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out) {
     extern __shared__ __align__(16) char smem[];
@@ -211,8 +213,9 @@ zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, cons
     constexpr int kIlp = 2, kChunk = 256;
     float4* wbuf = reinterpret_cast<float4*>(smem + (kSmem ? cloud_smem(o.n_pts) : 0)) + (threadIdx.x >> 5) * 64;
     const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    const int n_warps = gridDim.x * kWarpsPerCta;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * warps_per_cta;
     const int N = o.n_pts;
     const float fW = (float)cam.W, fH = (float)cam.H;
     const int n_chunks = (N + kChunk - 1) / kChunk;
@@ -295,7 +298,7 @@ zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, cons
 // Violation count only (pre-filter pass): exact part of the feature kernel, depth gather only.
 // ---------------------------------------------------------------------------------------
 template <bool kSmem>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 zs_k_violations(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
                 int n, int32_t* __restrict__ viol_out) {
     extern __shared__ __align__(16) char smem[];
@@ -303,8 +306,9 @@ zs_k_violations(obj_view o, zs_cam cam, const float4* __restrict__ frame, const 
     float* sV;
     stage_cloud<kSmem>(o, sA, sB, sV, smem);
     const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    const int n_warps = gridDim.x * kWarpsPerCta;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * warps_per_cta;
     const int N = o.n_pts;
     const float fW = (float)cam.W, fH = (float)cam.H;
     const float* frame_d = reinterpret_cast<const float*>(frame);
@@ -431,11 +435,25 @@ zs_k_filter(const int32_t* __restrict__ viol, int n, float n_pts_f, float th, in
     }
 }
 
-int grid_for(const zs_ctx* ctx, int n, int ctas_per_sm) {
-    int need = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+// CTA shape for the cloud-staging kernels: as many 8-warp CTAs per SM as shared memory allows (<= 4, the
+// register limit at 64 regs/thread); when the cloud is so large that fewer fit, grow the CTA instead so
+// that about 32 warps per SM share each staged copy.  `per_warp` = extra shared memory per warp.
+struct cta_shape { int threads, ctas_per_sm; size_t smem; };
+cta_shape shape_for(size_t cloud_bytes, size_t per_warp) {
+    for (int ctas = 4; ctas >= 1; --ctas) {
+        const int warps = 32 / ctas;                                  // 8, 10->8.., keep multiples that divide 32
+        if (32 % ctas) continue;
+        const size_t smem = cloud_bytes + per_warp * warps;
+        if ((smem + 1024) * ctas <= 220 * 1024) return cta_shape{warps * 32, ctas, smem};
+    }
+    return cta_shape{1024, 1, cloud_bytes + per_warp * 32};
+}
+
+int grid_for(const zs_ctx* ctx, long long n, int ctas_per_sm, int warps_per_cta = kWarpsPerCta) {
+    long long need = (n + warps_per_cta - 1) / warps_per_cta;
     int full = ctx->sm_count * ctas_per_sm;
     if (need >= full) return full;
-    return need < 1 ? 1 : need;
+    return need < 1 ? 1 : (int)need;
 }
 
 constexpr size_t kCloudSmemMax = 200 * 1024;
@@ -475,14 +493,13 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
     if (!feat_out || ((uintptr_t)feat_out & 15) || (uv_out && ((uintptr_t)uv_out & 7)))
         return zs_fail(ctx, ZS_ERR_INVALID, "feat_out must be 16-byte aligned (uv_out 8)");
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t stage = feat_dtype == ZS_F32 ? (size_t)kWarpsPerCta * 1024 : 0;   // fp32 store staging, 1 KB per warp
     const bool in_smem = cloud_smem(o.n_pts) <= kCloudSmemMax;
-    const size_t smem = (in_smem ? cloud_smem(o.n_pts) : 0) + stage;
     const bool aux = uv_out || mask_out || viol_out;
-    const size_t reg_limit = 4;                 // <= 64 registers per thread at 256 threads per CTA
-    const int ctas_per_sm = in_smem ? (int)max((size_t)1, min(reg_limit, (220 * 1024) / (smem + 1024))) : (int)reg_limit;
+    const cta_shape cs = shape_for(in_smem ? cloud_smem(o.n_pts) : 0, feat_dtype == ZS_F32 ? 1024 : 0);   // fp32 store staging: 1 KB/warp
+    const size_t smem = cs.smem;
+    const int threads = cs.threads;
     const long long units = aux ? n_keep : (long long)n_keep * ((o.n_pts + 255) / 256);
-    const int grid = grid_for(ctx, (int)min(units, (long long)1 << 30), ctas_per_sm);
+    const int grid = grid_for(ctx, units, cs.ctas_per_sm, threads / 32);
     cudaStream_t st = (cudaStream_t)stream;
     const float4* frame = ctx->frame.packed;
 #define ZS_LAUNCH_FEAT(BF, SM)                                                                          \
@@ -490,12 +507,12 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
         if (aux) {                                                                                      \
             rc = opt_in_smem(ctx, zs_k_features<BF, SM, true>, smem);                          \
             if (rc) return rc;                                                                          \
-            zs_k_features<BF, SM, true><<<grid, kThreads, smem, st>>>(                         \
+            zs_k_features<BF, SM, true><<<grid, threads, smem, st>>>(                         \
                 o, cam, frame, poses, keep_idx, n_keep, feat_out, uv_out, mask_out, viol_out);          \
         } else {                                                                                        \
             rc = opt_in_smem(ctx, zs_k_features_hot<BF, SM>, smem);                            \
             if (rc) return rc;                                                                          \
-            zs_k_features_hot<BF, SM><<<grid, kThreads, smem, st>>>(o, cam, frame, poses,      \
+            zs_k_features_hot<BF, SM><<<grid, threads, smem, st>>>(o, cam, frame, poses,      \
                                                                               keep_idx, n_keep, feat_out); \
         }                                                                                               \
     } while (0)
@@ -514,17 +531,16 @@ extern "C" int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int 
     if (rc) return rc;
     if (n < 0 || !viol_out) return zs_fail(ctx, ZS_ERR_INVALID, "n %d", n);
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t smem = (size_t)o.n_pts * 36;
-    const bool in_smem = smem <= kCloudSmemMax;
-    const int ctas_per_sm = in_smem ? (int)max((size_t)1, min((size_t)4, (220 * 1024) / (smem + 1024))) : 4;
-    const int grid = grid_for(ctx, n, ctas_per_sm);
+    const bool in_smem = cloud_smem(o.n_pts) <= kCloudSmemMax;
+    const cta_shape cs = shape_for(in_smem ? cloud_smem(o.n_pts) : 0, 0);
+    const int grid = grid_for(ctx, n, cs.ctas_per_sm, cs.threads / 32);
     cudaStream_t st = (cudaStream_t)stream;
     if (in_smem) {
-        rc = opt_in_smem(ctx, zs_k_violations<true>, smem);
+        rc = opt_in_smem(ctx, zs_k_violations<true>, cs.smem);
         if (rc) return rc;
-        zs_k_violations<true><<<grid, kThreads, smem, st>>>(o, cam, ctx->frame.packed, poses, n, viol_out);
+        zs_k_violations<true><<<grid, cs.threads, cs.smem, st>>>(o, cam, ctx->frame.packed, poses, n, viol_out);
     } else {
-        zs_k_violations<false><<<grid, kThreads, 0, st>>>(o, cam, ctx->frame.packed, poses, n, viol_out);
+        zs_k_violations<false><<<grid, cs.threads, 0, st>>>(o, cam, ctx->frame.packed, poses, n, viol_out);
     }
     ZS_LAUNCHED(ctx);
     return ZS_OK;
