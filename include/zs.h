@@ -156,6 +156,13 @@ ZS_API int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat_bf16, in
 ZS_API int zs_topk(zs_ctx* ctx, const float* scores, int n, int k, int index_base, const int32_t* index_map,
             float* s_out, int32_t* i_out, void* stream);
 
+/* Batched ADD / ADI pose error of every hypothesis against one ground-truth pose; replaces the Python loop
+ * `[err_func(R, t, R_gt, t_gt, model_points) for mat in poses_all]` (online_learning.py:452, err_func = add | adi
+ * from zephyr.utils.metrics, :32,337-339).  gt_pose [dev] float32 [12] (R|t rows), pts [dev] float32 (n_pts,3),
+ * symmetric != 0 selects ADI (nearest neighbour).  err_out [dev] float32 [n], metres. */
+ZS_API int zs_pose_errors(zs_ctx* ctx, const float* poses, int n, const float* gt_pose, const float* pts, int n_pts,
+                   int symmetric, float* err_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,6 +219,17 @@ class ZsContext:
                                         h2.data_ptr(), self._stream()), "zs_pool_debug")
         return pooled, h1.view(n, N, 64), h2.view(n, N, 128)
 
+    def pose_errors(self, poses12, gt_pose, points, symmetric: bool) -> torch.Tensor:
+        """ADD (symmetric=False) or ADI (True) of every hypothesis against ``gt_pose`` (4,4) -> (n,) float32 metres."""
+        pts = _dev_f32(points, self.device)
+        gt = poses_to_rt12(torch.as_tensor(gt_pose).reshape(1, 4, 4), self.device)
+        n = poses12.shape[0]
+        err = torch.empty((n,), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.zs_pose_errors(self.h, poses12.data_ptr() if n else None, n, gt.data_ptr(), pts.data_ptr(),
+                                         pts.shape[0], int(bool(symmetric)), err.data_ptr(), self._stream()),
+                 "zs_pose_errors")
+        return err
+
     def topk(self, scores: torch.Tensor, k: int, index_base: int = 0, index_map: Optional[torch.Tensor] = None):
         """Top-k by (score desc, index asc).  Returned index = index_map[i] (if given) + index_base."""
         s = torch.empty((k,), dtype=torch.float32, device=self.device)

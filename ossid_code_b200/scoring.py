@@ -108,6 +108,7 @@ class FrameScorer:
         self._pooled = None
         self._scores = None
         self._resident = None
+        self.forced_rank_world = None
         self.stage_events = None     # set to [] to record (stage, units, start_event, end_event) per launch group
 
     def _mark(self, stage, units, prev=None):
@@ -132,6 +133,8 @@ class FrameScorer:
 
     # -- distributed plumbing ---------------------------------------------------------
     def _rank_world(self):
+        if self.forced_rank_world is not None:        # tests: emulate rank r of P on one device, no process group
+            return self.forced_rank_world
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             return dist.get_rank(self.group), dist.get_world_size(self.group)
@@ -223,7 +226,7 @@ class FrameScorer:
             top_i.append(ti)
         S, I = torch.stack(top_s), torch.stack(top_i)
         rank, world = self._rank_world()
-        if world > 1:
+        if world > 1 and self.forced_rank_world is None:
             S, I = allgather_topk(S, I, k, self.group)
         return S, I
 
