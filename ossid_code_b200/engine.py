@@ -27,12 +27,21 @@ def _dev_f32(x, device) -> torch.Tensor:
 
 
 def poses_to_rt12(transforms, device) -> torch.Tensor:
-    """(M,4,4) any float dtype -> (M,12) float32 rows of (R|t) on ``device`` (include/zs.h)."""
+    """(M,4,4) any float dtype -> (M,12) float32 rows of (R|t) on ``device`` (include/zs.h).
+
+    The whole (M,16) block is copied as is (asynchronously when the source is pinned) and sliced / cast
+    once to float32 on the device; IEEE round-to-nearest either side, so the values equal a host cast.
+    """
     t = torch.as_tensor(transforms)
     if t.ndim != 3 or t.shape[1:] != (4, 4):
         raise ValueError(f"pose hypotheses must be (M,4,4), got {tuple(t.shape)}")
-    t = t[:, :3, :4].to(torch.float32).reshape(t.shape[0], 12).contiguous()
-    return t.to(device, non_blocking=True)
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    dev = torch.device(device)
+    if dev.type == "cpu":
+        return t[:, :3, :4].to(torch.float32).reshape(t.shape[0], 12).contiguous()
+    t = t.contiguous().to(dev, non_blocking=True)
+    return t[:, :3, :4].to(torch.float32).reshape(t.shape[0], 12).contiguous()
 
 
 class ZsContext:

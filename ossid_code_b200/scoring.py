@@ -151,13 +151,18 @@ class FrameScorer:
         res = []
         for o, ob in enumerate(objects):
             slot = o % 64
-            pts, cols, nrms = (torch.as_tensor(ob[key]) for key in ("model_points", "model_colors", "model_normals"))
-            if self.reorder_points:
-                perm = ob.get("_zs_order")
-                if perm is None:                      # cached on the object dict: clouds are reused frame after frame
-                    perm = torch.from_numpy(spatial_order(pts.cpu().numpy()))
-                    ob["_zs_order"] = perm
-                pts, cols, nrms = pts[perm], cols[perm], nrms[perm]
+            host = ob.get("_zs_host")
+            if host is None:
+                # clouds are static assets (the reference preloads them once, online_learning.py:303-311): keep a
+                # float32, Morton-ordered, pinned host copy so that every frame's upload is one async copy each
+                pts, cols, nrms = (torch.as_tensor(ob[key]).to(torch.float32) for key in
+                                   ("model_points", "model_colors", "model_normals"))
+                if self.reorder_points:
+                    perm = torch.from_numpy(spatial_order(pts.numpy()))
+                    pts, cols, nrms = pts[perm], cols[perm], nrms[perm]
+                host = tuple(t.contiguous().pin_memory() for t in (pts, cols, nrms))
+                ob["_zs_host"] = host
+            pts, cols, nrms = host
             ctx.set_object(slot, pts, cols, nrms)
             M = len(ob["pose_hypos"])
             lo, hi = shard_range(M, rank, world)
@@ -236,3 +241,36 @@ class FrameScorer:
         self.upload(img_u8, depth, cam_K, objects, weight_of)
         S, I = self.run_resident()
         return S.cpu().numpy(), I.cpu().numpy()
+
+    def score_frames(self, frames: List[dict], weight_of=lambda o: 0, depth: int = 2):
+        """Stream of frames (BASELINE.json config 5: multi-frame scoring between finetune steps).
+
+        ``frames``: dicts with ``img`` (uint8), ``depth``, ``cam_K``, ``objects``.  Uploads, kernels and the
+        read-back of each frame's top-k are all asynchronous; the host only blocks when ``depth`` frames are in
+        flight, so the copies of frame f+1 overlap the kernels of frame f.  Returns a list of
+        ``(scores (n_obj,k), indices (n_obj,k))`` numpy pairs, one per frame.  With the free-space pre-filter
+        enabled (inconst_ratio_th < 100) each frame still synchronises once per object to read the kept count.
+        """
+        stream = torch.cuda.current_stream(self.ctx.device)
+        inflight, out = [], []
+
+        def drain():
+            ev, s_h, i_h = inflight.pop(0)
+            ev.synchronize()
+            out.append((s_h.numpy().copy(), i_h.numpy().copy()))
+
+        for fr in frames:
+            self.upload(fr["img"], fr["depth"], fr["cam_K"], fr["objects"], weight_of)
+            S, I = self.run_resident()
+            s_h = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
+            i_h = torch.empty(I.shape, dtype=I.dtype, pin_memory=True)
+            s_h.copy_(S, non_blocking=True)
+            i_h.copy_(I, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            inflight.append((ev, s_h, i_h))
+            if len(inflight) >= depth:
+                drain()
+        while inflight:
+            drain()
+        return out

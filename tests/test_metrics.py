@@ -29,7 +29,7 @@ def test_oracle_add_adi_against_kdtree():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_pts,n_hypo", [(300, 40), (1000, 2000), (1, 3), (33, 1)])
+@pytest.mark.parametrize("n_pts,n_hypo", [(300, 40), (1000, 300), (1, 3), (33, 1)])
 def test_kernel_pose_errors_match_oracle(n_pts, n_hypo):
     from ossid_code_b200 import metrics
     P, G, pts = _case(5, n_pts, n_hypo)
