@@ -326,6 +326,17 @@ def main():
                                       "ms_per_launch": k_ms, "hypotheses_per_s": p_big.shape[0] / (k_ms * 1e-3)}
     del buf
 
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):                     # measured DRAM traffic per launch, valid for the profiled launch shape only
+        tr = json.load(open(tpath))
+        if tr.get("workload") == args.workload and tr.get("precision") == args.precision and world == 1:
+            for key, stage in (("roofline", "zs_pool"), ("roofline_features", "zs_features")):
+                if key in roof and stage in tr:
+                    roof[key]["traffic"] = tr[stage]["dram_read_bytes"] + tr[stage]["dram_write_bytes"]
+                    roof[key]["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, bytes per launch of 10,000 hypotheses)"
+    for key, per_unit in (("roofline", None), ("roofline_features", 48 + n_pts * 8 * fbytes)):
+        if key in roof and per_unit:
+            roof[key]["algorithmic_bytes_per_launch"] = per_unit * stages["features"]["units"] / n_pts / stages["features"]["calls"]
     line = {
         "metric": "hypotheses_scored_per_sec", "value": value, "unit": "hypotheses/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
