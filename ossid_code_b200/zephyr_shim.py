@@ -113,10 +113,13 @@ class PointNet2SSG(torch.nn.Module):
         return super().load_state_dict(sd, strict=strict)
 
     def _sync_weights(self, ctx):
+        # re-upload when the parameters changed or when another model instance has taken this slot meanwhile
         key = (ctx.index, tuple(p._version for p in self.state_dict().values()))
-        if self._uploaded != key:
+        owners = ctx.__dict__.setdefault("weight_slot_owner", {})
+        if self._uploaded != key or owners.get(self._slot) != id(self):
             ctx.set_weights(self._slot, W.fold_state_dict(self.state_dict()))
             self._uploaded = key
+            owners[self._slot] = id(self)
 
     def forward(self, batch):
         if self.training:

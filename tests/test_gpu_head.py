@@ -117,3 +117,19 @@ def test_sharded_scoring_top1_independent_of_gpu_count(ctx, world):
     tie = [int(x) for x in I1[1] if x in (7, 100)]
     if len(tie) == 2:
         assert tie == [7, 100], "tie must resolve to the lower hypothesis index"
+
+
+def test_many_model_instances_do_not_share_stale_weights(ctx):
+    """More PointNet2SSG instances than weight slots: each forward must use its own weights."""
+    from ossid_code_b200 import zephyr_shim
+    x = (torch.randn(6, 64, 8, generator=torch.Generator().manual_seed(0)) * 0.5).to(ctx.device)
+    models, refs = [], []
+    for seed in range(6):
+        m = zephyr_shim.PointNet2SSG(8, None, 1)
+        m.load_state_dict(weights.seeded_state_dict(seed))
+        models.append(m.to(0).eval())
+        refs.append(zo.scorer(x.cpu(), weights.seeded_folded(seed)))
+    for rnd in range(2):
+        for m, ref in zip(models, refs):
+            got = m({"point_x": x}).reshape(-1).cpu()
+            assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-6
