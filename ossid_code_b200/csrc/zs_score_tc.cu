@@ -29,6 +29,24 @@
 
 namespace {
 
+// Optional per-role wait accounting (build with -DZS_TC_PROF; tools/k2_prof.py reads the counters out of dbg_h2).
+#ifdef ZS_TC_PROF
+#include <cstdlib>
+__device__ int g_exp = 0;          // experiment bits (ZS_TC_EXPERIMENT): 1 = no operand stores, 2 = no bias loads, 4 = no TMEM loads in max-pool
+#define EXP(bit) (g_exp & (bit))
+constexpr bool kDbgDump = false;
+#define PROF_DECL long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64()
+#define PROF_WAIT(slot, stmt) do { const long long t_ = clock64(); stmt; prof[slot] += clock64() - t_; } while (0)
+#define PROF_DUMP(base, cnt) do { if (dbg_h2) { long long* o_ = reinterpret_cast<long long*>(dbg_h2) + (size_t)blockIdx.x * 24 + (base); \
+        o_[0] = clock64() - prof_t0; for (int q_ = 0; q_ < (cnt); ++q_) o_[1 + q_] = prof[q_]; } } while (0)
+#else
+#define EXP(bit) false
+constexpr bool kDbgDump = true;
+#define PROF_DECL
+#define PROF_WAIT(slot, stmt) stmt
+#define PROF_DUMP(base, cnt)
+#endif
+
 constexpr int kTile = 128;               // points per tile
 constexpr int kThreadsTc = 320;
 constexpr int kStages = 3;
@@ -94,6 +112,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// One elected lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler then knows the region is
+// single-threaded and issues UTCHMMA / UTCBAR without a per-instruction ELECT + BRA.U.ANY guard loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -125,6 +150,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2;
+// The same descriptor split in words: low = start address | leading byte offset, high = stride byte offset | version |
+// layout.  desc_at() adds a byte offset to the start-address field (no carry: shared addresses stay below 256 KB).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3fff) | (((lbo_bytes >> 4) & 0x3fff) << 16); }
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) { return ((sbo_bytes >> 4) & 0x3fff) | (1u << 14) | (layout << 29); }
+__device__ __forceinline__ uint64_t desc_at(uint32_t lo, uint32_t hi, uint32_t off_bytes) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(d) : "r"(lo + (off_bytes >> 4)), "r"(hi));
+    return d;
+}
 
 // Instruction descriptor: fp32 accumulate, bf16 x bf16, both operands K-major.
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -160,14 +194,17 @@ __device__ __forceinline__ void epi_store32(const uint32_t (&v)[32], const float
                                             uint32_t r, uint32_t chunk0) {
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
-        const float4 bA = *reinterpret_cast<const float4*>(bias + c8 * 8);
-        const float4 bB = *reinterpret_cast<const float4*>(bias + c8 * 8 + 4);
+        float4 bA = make_float4(0.f, 0.f, 0.f, 0.f), bB = bA;
+        if (!EXP(2)) {
+            bA = *reinterpret_cast<const float4*>(bias + c8 * 8);
+            bB = *reinterpret_cast<const float4*>(bias + c8 * 8 + 4);
+        }
         uint4 o;
         o.x = bias_relu_pack(v[c8 * 8 + 0], v[c8 * 8 + 1], make_float2(bA.x, bA.y));
         o.y = bias_relu_pack(v[c8 * 8 + 2], v[c8 * 8 + 3], make_float2(bA.z, bA.w));
         o.z = bias_relu_pack(v[c8 * 8 + 4], v[c8 * 8 + 5], make_float2(bB.x, bB.y));
         o.w = bias_relu_pack(v[c8 * 8 + 6], v[c8 * 8 + 7], make_float2(bB.z, bB.w));
-        *reinterpret_cast<uint4*>(tile + sw128_off(r, chunk0 + c8)) = o;
+        if (!EXP(1)) *reinterpret_cast<uint4*>(tile + sw128_off(r, chunk0 + c8)) = o;
     }
 }
 __device__ __forceinline__ void dbg_dump32(float* __restrict__ dst, const uint32_t (&v)[32], const float* __restrict__ bias) {
@@ -247,52 +284,56 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
         }
     } else if (warp == 9) {
         // ===== MMA issuer (one thread) ============================================================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc_l1 = make_idesc(128, 64), idesc_128 = make_idesc(128, 128);
             mbar_wait(bar(BAR_W_FULL), 0);
+            PROF_DECL;
             tc_fence_after();
+            // Descriptors differ only in their 14-bit start-address field, so every MMA's pair is "base low word +
+            // immediate": the issuing thread must not spend more than ~64 cycles of dependent address arithmetic
+            // per MMA or it, not the tensor pipe, paces the kernel (tools/mma_probe.cu measures exactly that).
+            constexpr uint32_t hi_sw = desc_hi(1024, kLayoutSw128), hi_x = desc_hi(128, kLayoutNone);
+            const uint32_t w3_lo = desc_lo(sbase + kSmW3, 16), w2_lo = desc_lo(sbase + kSmW2, 16);
+            const uint32_t w1_lo = desc_lo(sbase + kSmW1, 1024);
             auto issue_l3 = [&](int it, int cb) {           // layer 3, channel block cb of tile `it`
                 const int q = it * 4 + cb, b = q % kD3Bufs, buf = it & 1;   // A3_FULL of tile `it` was awaited by the caller
-                mbar_wait(bar(BAR_D3_EMPTY + b), ((q / kD3Bufs) & 1) ^ 1);
+                const uint32_t a3_lo = desc_lo(sbase + kSmA3 + buf * 32768, 16), d3 = tmem + kColD3 + b * 128;
+                PROF_WAIT(1, mbar_wait(bar(BAR_D3_EMPTY + b), ((q / kD3Bufs) & 1) ^ 1));
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint32_t kb = k >> 2, kk = k & 3;
-                    const uint64_t da = make_desc(sbase + kSmW3 + (cb * 2 + kb) * 16384 + kk * 32, 16, 1024, kLayoutSw128);
-                    const uint64_t db = make_desc(sbase + kSmA3 + buf * 32768 + kb * 16384 + kk * 32, 16, 1024, kLayoutSw128);
-                    tc_mma(tmem + kColD3 + b * 128, da, db, idesc_128, k > 0);
+                    tc_mma(d3, desc_at(w3_lo, hi_sw, (cb * 2 + kb) * 16384 + kk * 32),
+                           desc_at(a3_lo, hi_sw, kb * 16384 + kk * 32), idesc_128, k > 0);
                 }
                 tc_commit(bar(BAR_D3_FULL + b));
                 if (cb == 3) tc_commit(bar(BAR_A3_EMPTY + buf));
             };
             for (int i = 0; i <= total; ++i) {
                 // H2 of tile i-1 is ready and D2 (which D1 aliases) has been drained by epilogue 2
-                if (i >= 1) mbar_wait(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1);
+                if (i >= 1) PROF_WAIT(0, mbar_wait(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1));
                 if (i < total) {
                     const int s = i % kStages;
-                    mbar_wait(bar(BAR_X_FULL + s), (i / kStages) & 1);
+                    PROF_WAIT(3, mbar_wait(bar(BAR_X_FULL + s), (i / kStages) & 1));
                     tc_fence_after();
                     const uint32_t xa = sbase + kSmX + s * 2048;
-                    const uint64_t da = make_desc(xa, (sbase + kSmZero) - xa, 128, kLayoutNone);
-                    const uint64_t db = make_desc(sbase + kSmW1, 1024, 128, kLayoutNone);
-                    tc_mma(tmem + kColD1, da, db, idesc_l1, 0);
+                    tc_mma(tmem + kColD1, desc_at(desc_lo(xa, (sbase + kSmZero) - xa), hi_x, 0), desc_at(w1_lo, hi_x, 0), idesc_l1, 0);
                     tc_commit(bar(BAR_X_EMPTY + s));
                     tc_commit(bar(BAR_D1_FULL));
                 }
                 if (i >= 1) { issue_l3(i - 1, 0); }
                 if (i < total) {
-                    mbar_wait(bar(BAR_A2_FULL), i & 1);
+                    const uint32_t a2_lo = desc_lo(sbase + kSmA3 + (i & 1) * 32768, 16);
+                    PROF_WAIT(2, mbar_wait(bar(BAR_A2_FULL), i & 1));
                     tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t da = make_desc(sbase + kSmA3 + (i & 1) * 32768 + kk * 32, 16, 1024, kLayoutSw128);
-                        const uint64_t db = make_desc(sbase + kSmW2 + kk * 32, 16, 1024, kLayoutSw128);
-                        tc_mma(tmem + kColD2, da, db, idesc_128, kk > 0);
-                    }
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma(tmem + kColD2, desc_at(a2_lo, hi_sw, kk * 32), desc_at(w2_lo, hi_sw, kk * 32), idesc_128, kk > 0);
                     tc_commit(bar(BAR_D2_FULL));
                 }
                 if (i >= 1) { issue_l3(i - 1, 1); issue_l3(i - 1, 2); issue_l3(i - 1, 3); }
             }
+            PROF_DUMP(0, 4);
         }
     } else if (warp < 4) {
         // ===== front epilogues: D1 -> H1 (bf16, swizzled), D2 -> H2 ================================
@@ -300,13 +341,14 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
         const float* b1 = reinterpret_cast<const float*>(sm + kSmB1);
         const float* b2 = reinterpret_cast<const float*>(sm + kSmB2);
+        PROF_DECL;
         for (int i = 0; i < total; ++i) {
             const int buf = i & 1, j = i / T, tt = i - j * T;
             const long long row0 = (long long)(pair + j * n_pairs) * N + (long long)tt * kTile;
             const int valid = min(kTile, N - tt * kTile);
             uint8_t* a3 = sm + kSmA3 + buf * 32768;
-            mbar_wait(bar(BAR_A3_EMPTY + buf), ((i >> 1) & 1) ^ 1);     // layer 3 of tile i-2 has released this buffer
-            mbar_wait(bar(BAR_D1_FULL), i & 1);
+            PROF_WAIT(0, mbar_wait(bar(BAR_A3_EMPTY + buf), ((i >> 1) & 1) ^ 1));     // layer 3 of tile i-2 has released this buffer
+            PROF_WAIT(1, mbar_wait(bar(BAR_D1_FULL), i & 1));
             tc_fence_after();
             {   // layer 1: 64 channels = two 32-column loads in flight, one wait
                 uint32_t v0[32], v1[32];
@@ -315,7 +357,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 tc_wait_ld();
                 epi_store32(v0, b1, a3, r, 0);
                 epi_store32(v1, b1 + 32, a3, r, 4);
-                if (dbg_h1 && half == 0 && (int)r < valid) {
+                if (kDbgDump && dbg_h1 && half == 0 && (int)r < valid) {
                     dbg_dump32(dbg_h1 + (row0 + r) * 64, v0, b1);
                     dbg_dump32(dbg_h1 + (row0 + r) * 64 + 32, v1, b1 + 32);
                 }
@@ -325,7 +367,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             named_bar(1, 128);
             if (tid == 0) mbar_arrive(bar(BAR_A2_FULL));
 
-            mbar_wait(bar(BAR_D2_FULL), i & 1);
+            PROF_WAIT(2, mbar_wait(bar(BAR_D2_FULL), i & 1));
             tc_fence_after();
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {                            // layer 2: 2 x 64 channels (= K halves of layer 3)
@@ -335,7 +377,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 tc_wait_ld();
                 epi_store32(v0, b2 + kb * 64, a3 + kb * 16384, r, 0);
                 epi_store32(v1, b2 + kb * 64 + 32, a3 + kb * 16384, r, 4);
-                if (dbg_h2 && half == 0 && (int)r < valid) {
+                if (kDbgDump && dbg_h2 && half == 0 && (int)r < valid) {
                     dbg_dump32(dbg_h2 + (row0 + r) * 128 + kb * 64, v0, b2 + kb * 64);
                     dbg_dump32(dbg_h2 + (row0 + r) * 128 + kb * 64 + 32, v1, b2 + kb * 64 + 32);
                 }
@@ -345,12 +387,14 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             named_bar(1, 128);
             if (tid == 0) mbar_arrive(bar(BAR_A3_FULL + buf));
         }
+        if (tid == 0) PROF_DUMP(8, 3);
     } else {
         // ===== max-pool epilogue: D3[channel lane][point column] -> running max -> pooled ===========
         const int wq = warp - 4;                                        // TMEM lane quadrant == warp % 4
         const int L = wq * 32 + lane;                                   // channel within the 128-channel block
         const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
         float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        PROF_DECL;
         for (int i = 0; i < total; ++i) {
             const int j = i / T, tt = i - j * T;
             const int h = pair + j * n_pairs;
@@ -358,13 +402,13 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 const int q = i * 4 + cb, b = q % kD3Bufs;
-                mbar_wait(bar(BAR_D3_FULL + b), (q / kD3Bufs) & 1);
+                PROF_WAIT(0, mbar_wait(bar(BAR_D3_FULL + b), (q / kD3Bufs) & 1));
                 tc_fence_after();
                 float mm = m[cb];
                 {
                     uint32_t v0[32], v1[32], v2[32], v3[32];           // all 128 point columns in flight, one wait
                     const uint32_t a = lane_addr + kColD3 + b * 128;
-                    tc_ld32(a, v0); tc_ld32(a + 32, v1); tc_ld32(a + 64, v2); tc_ld32(a + 96, v3);
+                    if (!EXP(4)) { tc_ld32(a, v0); tc_ld32(a + 32, v1); tc_ld32(a + 64, v2); tc_ld32(a + 96, v3); }
                     tc_wait_ld();
                     if (valid == kTile) {
                         float q[4] = {mm, -INFINITY, -INFINITY, -INFINITY};
@@ -391,6 +435,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 m[cb] = mm;
             }
         }
+        if (tid == 128) PROF_DUMP(16, 1);
     }
 
     // ---- teardown --------------------------------------------------------------------------------
@@ -447,6 +492,9 @@ static int launch_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, in
                      float* dbg_h1, float* dbg_h2, cudaStream_t st) {
     const zs_weights& w = ctx->w[slot];
     ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmAlloc));
+#ifdef ZS_TC_PROF
+    { const char* e = getenv("ZS_TC_EXPERIMENT"); int v = e ? atoi(e) : 0; cudaMemcpyToSymbolAsync(g_exp, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st); }
+#endif
     int grid = ctx->sm_count & ~1;                 // CTA pairs
     if (grid > 2 * n) grid = 2 * n;
     zs_k_mlp_tc<<<grid, kThreadsTc, kSmAlloc, st>>>(feat, n, n_pts, reinterpret_cast<const uint8_t*>(w.bf16), w.f32,
