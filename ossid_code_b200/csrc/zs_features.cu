@@ -199,19 +199,31 @@ zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const fl
 // ---------------------------------------------------------------------------------------
 // Hot variant: features only (no mask / uv / violation outputs).  Work unit = 256-point chunk of a
 // hypothesis (short last wave); each lane carries kIlp points per iteration so that kIlp frame
-// gathers are in flight per warp (the kernel is otherwise bound by the latency of that gather).
-// Arithmetic is the same as zs_k_features<.,.,false>.
+// gathers are in flight per warp.  The body is branch-free: out-of-range lanes of the last
+// iteration recompute the chunk's last point and only the store is predicated; a point that does
+// not project into the frame gathers pixel 0 and has its features zeroed by a select at the end
+// (same values as zs_k_features<.,.,false>, which skips the work instead).  fp32 rows (32 B) leave
+// as one 256-bit store per lane: every lane writes one full sector, the warp 1 KB contiguous.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_f32_row(float* p, float4 lo, float4 hi, bool aligned32) {
+    if (aligned32) {
+        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w),
+                     "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+    } else {
+        st_cs_f4(reinterpret_cast<float4*>(p), lo);
+        st_cs_f4(reinterpret_cast<float4*>(p) + 1, hi);
+    }
+}
+
 template <bool kBf16, bool kSmem>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
-                  const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out) {
+                  const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out, int aligned32) {
     extern __shared__ __align__(16) char smem[];
     float4 *sA, *sB;
     float* sV;
     stage_cloud<kSmem>(o, sA, sB, sV, smem);
     constexpr int kIlp = 2, kChunk = 256;
-    float4* wbuf = reinterpret_cast<float4*>(smem + (kSmem ? cloud_smem(o.n_pts) : 0)) + (threadIdx.x >> 5) * 64;
     const int lane = threadIdx.x & 31;
     const int warps_per_cta = blockDim.x >> 5;
     const int warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
@@ -228,66 +240,53 @@ zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, cons
         const zs_pose T = zs_load_pose(poses, h);
         const size_t row = (size_t)hk * N;
         for (int p0 = p_begin; p0 < p_end; p0 += 32 * kIlp) {
-            float4 a[kIlp], b[kIlp], px[kIlp];
-            float x[kIlp], y[kIlp], z[kIlp];
-            int ui[kIlp], vi[kIlp];
+            float4 a[kIlp], px[kIlp];
+            float x[kIlp], y[kIlp], z[kIlp], uf[kIlp], vf[kIlp];
+            int q[kIlp];
             bool valid[kIlp];
 #pragma unroll
             for (int j = 0; j < kIlp; ++j) {                 // phase 1: exact projection, issue the gather
-                const int p = p0 + j * 32 + lane;
-                valid[j] = false;
-                ui[j] = vi[j] = 0;
-                px[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p < p_end) {
-                    a[j] = kSmem ? sA[p] : __ldg(sA + p);
-                    float ur, vr;
-                    zs_transform(T, a[j].x, a[j].y, a[j].z, x[j], y[j], z[j]);
-                    zs_project(cam, x[j], y[j], z[j], ur, vr);
-                    valid[j] = (z[j] > 0.f) && (z[j] <= kFltMax) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
-                    if (valid[j]) {
-                        ui[j] = (int)ur;
-                        vi[j] = (int)vr;
-                        px[j] = __ldg(frame + (size_t)vi[j] * cam.W + ui[j]);   // {d_obs, H, S, V}
-                    }
-                }
+                q[j] = min(p0 + j * 32 + lane, p_end - 1);
+                a[j] = kSmem ? sA[q[j]] : __ldg(sA + q[j]);
+                float ur, vr;
+                zs_transform(T, a[j].x, a[j].y, a[j].z, x[j], y[j], z[j]);
+                zs_project(cam, x[j], y[j], z[j], ur, vr);
+                valid[j] = (z[j] > 0.f) && (z[j] <= kFltMax) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
+                uf[j] = valid[j] ? ur : 0.f;
+                vf[j] = valid[j] ? vr : 0.f;
+                px[j] = __ldg(frame + ((int)vf[j] * cam.W + (int)uf[j]));   // {d_obs, H, S, V}; pixel 0 when invalid
             }
 #pragma unroll
             for (int j = 0; j < kIlp; ++j) {                 // phase 2: residual features, store
                 const int p = p0 + j * 32 + lane;
-                const int n_act = p_end - (p0 + j * 32);      // warp-uniform
-                if (n_act <= 0) continue;
-                float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f, f5 = 0.f, f6 = 0.f;
-                if (valid[j]) {
-                    b[j] = kSmem ? sB[p] : __ldg(sB + p);
-                    const float vm = kSmem ? sV[p] : __ldg(sV + p);
-                    const float nx = fmaf(T.r[0], b[j].x, fmaf(T.r[1], b[j].y, T.r[2] * b[j].z));
-                    const float ny = fmaf(T.r[4], b[j].x, fmaf(T.r[5], b[j].y, T.r[6] * b[j].z));
-                    const float nz = fmaf(T.r[8], b[j].x, fmaf(T.r[9], b[j].y, T.r[10] * b[j].z));
-                    const float dot = -fmaf(x[j], nx, fmaf(y[j], ny, z[j] * nz));
-                    const bool vd = (px[j].x > 0.f) && (px[j].x <= kFltMax);
-                    float dH = px[j].y - a[j].w;
-                    dH = dH > 0.5f ? dH - 1.0f : dH;
-                    dH = dH < -0.5f ? dH + 1.0f : dH;
-                    f0 = ((float)ui[j] - cam.cx) * cam.inv_fx;
-                    f1 = ((float)vi[j] - cam.cy) * cam.inv_fy;
-                    f2 = dH;
-                    f3 = px[j].z - b[j].w;
-                    f4 = px[j].w - vm;
-                    f5 = vd ? xsub(px[j].x, z[j]) : 0.f;
-                    const float c = dot * rsqrt_fast(fmaf(x[j], x[j], fmaf(y[j], y[j], z[j] * z[j]))) *
-                                    rsqrt_fast(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
-                    f6 = (fabsf(c) <= kFltMax) ? c : 0.f;
-                }
+                const float4 b = kSmem ? sB[q[j]] : __ldg(sB + q[j]);
+                const float vm = kSmem ? sV[q[j]] : __ldg(sV + q[j]);
+                const float nx = fmaf(T.r[0], b.x, fmaf(T.r[1], b.y, T.r[2] * b.z));
+                const float ny = fmaf(T.r[4], b.x, fmaf(T.r[5], b.y, T.r[6] * b.z));
+                const float nz = fmaf(T.r[8], b.x, fmaf(T.r[9], b.y, T.r[10] * b.z));
+                const float dot = -fmaf(x[j], nx, fmaf(y[j], ny, z[j] * nz));
+                const bool vd = (px[j].x > 0.f) && (px[j].x <= kFltMax);
+                float dH = px[j].y - a[j].w;
+                dH = dH > 0.5f ? dH - 1.0f : dH;
+                dH = dH < -0.5f ? dH + 1.0f : dH;
+                const float f0 = (uf[j] - cam.cx) * cam.inv_fx;
+                const float f1 = (vf[j] - cam.cy) * cam.inv_fy;
+                const float f3 = px[j].z - b.w;
+                const float f4 = px[j].w - vm;
+                const float f5 = vd ? xsub(px[j].x, z[j]) : 0.f;
+                const float c = dot * rsqrt_fast(fmaf(x[j], x[j], fmaf(y[j], y[j], z[j] * z[j]))) *
+                                rsqrt_fast(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+                const float f6 = (fabsf(c) <= kFltMax) ? c : 0.f;      // NaN / inf (degenerate pose) -> 0
                 if (kBf16) {
-                    if (p < p_end) {
-                        uint4 v;
-                        v.x = pack_bf16x2(f0, f1); v.y = pack_bf16x2(f2, f3);
-                        v.z = pack_bf16x2(f4, f5); v.w = pack_bf16x2(f6, 0.f);
-                        st_cs_u4(reinterpret_cast<uint4*>(feat_out) + row + p, v);
-                    }
+                    uint4 v;
+                    v.x = pack_bf16x2(f0, f1); v.y = pack_bf16x2(dH, f3);
+                    v.z = pack_bf16x2(f4, f5); v.w = pack_bf16x2(f6, 0.f);
+                    if (!valid[j]) v = make_uint4(0u, 0u, 0u, 0u);
+                    if (p < p_end) st_cs_u4(reinterpret_cast<uint4*>(feat_out) + row + p, v);
                 } else {
-                    store_f32_rows(wbuf, lane, reinterpret_cast<float4*>(feat_out) + (row + p0 + j * 32) * 2, n_act,
-                                   make_float4(f0, f1, f2, f3), make_float4(f4, f5, f6, 0.f));
+                    float4 lo = make_float4(f0, f1, dH, f3), hi = make_float4(f4, f5, f6, 0.f);
+                    if (!valid[j]) lo = hi = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p < p_end) st_f32_row(reinterpret_cast<float*>(feat_out) + (row + p) * 8, lo, hi, aligned32 != 0);
                 }
             }
         }
@@ -495,7 +494,7 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool in_smem = cloud_smem(o.n_pts) <= kCloudSmemMax;
     const bool aux = uv_out || mask_out || viol_out;
-    const cta_shape cs = shape_for(in_smem ? cloud_smem(o.n_pts) : 0, feat_dtype == ZS_F32 ? 1024 : 0);   // fp32 store staging: 1 KB/warp
+    const cta_shape cs = shape_for(in_smem ? cloud_smem(o.n_pts) : 0, (aux && feat_dtype == ZS_F32) ? 1024 : 0);   // fp32 store staging (side-output kernel): 1 KB/warp
     const size_t smem = cs.smem;
     const int threads = cs.threads;
     const long long units = aux ? n_keep : (long long)n_keep * ((o.n_pts + 255) / 256);
@@ -513,7 +512,8 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
             rc = opt_in_smem(ctx, zs_k_features_hot<BF, SM>, smem);                            \
             if (rc) return rc;                                                                          \
             zs_k_features_hot<BF, SM><<<grid, threads, smem, st>>>(o, cam, frame, poses,      \
-                                                                              keep_idx, n_keep, feat_out); \
+                                                                  keep_idx, n_keep, feat_out,          \
+                                                                  (((uintptr_t)feat_out & 31) == 0));  \
         }                                                                                               \
     } while (0)
     if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_FEAT(true, true); else ZS_LAUNCH_FEAT(true, false); }
