@@ -2,25 +2,33 @@
 // tensor cores (tcgen05.mma, bf16 operands, fp32 accumulators in TMEM), sm_100a only.
 // Reference call: model({"point_x": ...}), python/ossid/utils/zephyr_utils.py:34.
 //
-// Work split.  Persistent kernel, one CTA per SM.  CTAs come in pairs (2j, 2j+1) that walk the same
-// hypotheses; CTA `half` owns output channels [512*half, 512*half+512) of layer 3, whose bf16
-// weights (128 KB) stay resident in its shared memory for the whole launch.  Layers 1-2 (6 % of
-// the MACs) are recomputed by both CTAs of a pair, which keeps the two CTAs independent: no
-// cluster, no DSMEM, no cross-CTA reduction (the halves write disjoint channels of pooled[]).
+// Work split.  Persistent kernel, one CTA per SM, launched as clusters of two CTAs (the two SMs of a TPC) that
+// execute every MMA together (cta_group::2, M = 256): CTA `rank` supplies 128 rows of the M side and half of the
+// N side of each instruction and receives its own 128 accumulator lanes.  A pair walks the same hypotheses.
 //
-// Tile = 128 consecutive points of one hypothesis.
-//   L1  D1[128 pts x  64] = X [128 x 16(8 real + 8 zero)] . W1^T      M=128 N=64  K=16  (1 MMA)
-//   L2  D2[128 pts x 128] = H1[128 x 64]  . W2^T                      M=128 N=128 K=64  (4 MMAs)
-//   L3  D3[128 ch  x 128 pts] = W3blk[128 x 128] . H2^T, 4 channel blocks  M=128 N=128 K=128 (8 MMAs each)
+// Pair-tile = 256 consecutive points of one hypothesis; CTA `rank` owns points [128*rank, 128*rank+128) of it.
+//   L1  D1[own 128 pts x  64] = X [256 x 16(8 real + 8 zero)] . W1^T     M=256 N=64  K=16  (1 MMA;  W1 rows split 32/32)
+//   L2  D2[own 128 pts x 128] = H1[256 x 64]  . W2^T                     M=256 N=128 K=64  (4 MMAs; W2 rows split 64/64)
+//   L3  D3[own 128 ch  x 128 pts] = W3blk[256 ch x 128] . H2sub^T        M=256 N=128 K=128 (8 MMAs) for each of
+//       4 channel blocks x 2 point halves: the M side is the pair's 2 x 128 channels of block cb (CTA `rank` keeps
+//       channels [512*rank, 512*rank+512) of W3, 128 KB bf16, resident in its shared memory for the whole launch),
+//       the N side is points [64*h, 64*h+64) of EACH CTA's H2 tile.
+// So layers 1-2 are computed once per point (the single-CTA version recomputed them in both CTAs), every L3
+// instruction reads 4 KB of A + 2 KB of B per CTA instead of 4 + 4 (N = 128 single-CTA MMAs need all 128 B/clk of
+// shared-memory bandwidth), and the front epilogue handles half as many rows per point of work -- the kernel is
+// power-bound in sustained runs, so the energy per hypothesis is what sets the throughput.
 // L1/L2 put points on TMEM lanes, so the epilogue thread of a point holds its whole channel row and
 // writes it as the next layer's K-major, 128B-swizzled operand with 16-byte stores.  L3 puts
 // CHANNELS on lanes and points on columns, so max-over-points is a register-only reduction in the
 // thread that owns the channel; bias + ReLU commute with max and are applied once per hypothesis.
 //
-// Warp roles (320 threads): warps 0-3 front epilogues (D1 -> H1, D2 -> H2), warps 4-7 max-pool
+// Warp roles (320 threads per CTA): warps 0-3 front epilogues (D1 -> H1, D2 -> H2), warps 4-7 max-pool
 // epilogue (D3), warp 8 bulk-copy producer (weights once, then feature tiles, 3 stages), warp 9
-// TMEM allocator + single-thread MMA issuer.  Front of tile i+1 overlaps layer 3 of tile i; D3 is
-// triple-buffered in TMEM (cols: D1 0-63 inside D2 0-127, D3 128-255 / 256-383 / 384-511).  H1 aliases the H2
+// TMEM allocator and -- in the leader CTA (rank 0) only -- the single elected MMA-issuing thread.  Completion
+// of MMAs reaches both CTAs through multicast tcgen05.commit; "operand ready" / "accumulator drained" travel
+// the other way as mbarrier arrivals on the leader's barriers (count 2: one local, one remote arrive).
+// Front of pair-tile i+1 overlaps layer 3 of pair-tile i; D3 is triple-buffered in TMEM
+// (cols: D1 0-63 inside D2 0-127, D3 128-255 / 256-383 / 384-511).  H1 aliases the H2
 // buffer that the same tile's epilogue 2 overwrites afterwards, which is what makes two H2
 // buffers + the resident weights fit in 227 KB.
 #include <cuda.h>
@@ -47,15 +55,16 @@ constexpr bool kDbgDump = true;
 #define PROF_DUMP(base, cnt)
 #endif
 
-constexpr int kTile = 128;               // points per tile
+constexpr int kTile = 128;               // points per CTA per pair-tile
+constexpr int kPairTile = 2 * kTile;     // points per pair-tile
 constexpr int kThreadsTc = 320;
 constexpr int kStages = 3;
 
 // ---- shared-memory map (bytes from a 1024-aligned base) ---------------------------------------
 constexpr uint32_t kSmW3 = 0;                          // 4 blocks x 2 k-halves x 16 KB
-constexpr uint32_t kSmW2 = kSmW3 + 131072;             // 16 KB
-constexpr uint32_t kSmA3 = kSmW2 + 16384;              // 2 x 32 KB  (H2; first 16 KB doubles as H1)
-constexpr uint32_t kSmW1 = kSmA3 + 2 * 32768;          // 2 KB
+constexpr uint32_t kSmW2 = kSmW3 + 131072;             // 8 KB: this CTA's 64 rows of W2
+constexpr uint32_t kSmA3 = kSmW2 + 8192;               // 2 x 32 KB  (H2; first 16 KB doubles as H1)
+constexpr uint32_t kSmW1 = kSmA3 + 2 * 32768;          // 1 KB: this CTA's 32 rows of W1 (2 KB reserved)
 constexpr uint32_t kSmX = kSmW1 + 2048;                // 3 x 2 KB feature tiles
 constexpr uint32_t kSmZero = kSmX + kStages * 2048;    // 2 KB of zeros (upper K half of X)
 constexpr uint32_t kSmB1 = kSmZero + 2048;             // 64 floats
@@ -69,7 +78,8 @@ static_assert(kSmAlloc <= 232448, "exceeds 227 KB of shared memory per CTA");
 // barrier slots
 enum : int {
     BAR_W_FULL = 0, BAR_X_FULL = 1 /*3*/, BAR_X_EMPTY = 4 /*3*/, BAR_D1_FULL = 7, BAR_A2_FULL = 8, BAR_D2_FULL = 9,
-    BAR_A3_FULL = 10 /*2*/, BAR_A3_EMPTY = 12 /*2*/, BAR_D3_FULL = 14 /*3*/, BAR_D3_EMPTY = 17 /*3*/, BAR_COUNT = 20
+    BAR_A3_FULL = 10 /*2*/, BAR_A3_EMPTY = 12 /*2*/, BAR_D3_FULL = 14 /*3*/, BAR_D3_EMPTY = 17 /*3*/,
+    BAR_XP_FULL = 20 /*3: peer's feature tile landed (leader only)*/, BAR_WP_FULL = 23 /*peer's weights landed*/, BAR_COUNT = 24
 };
 
 // TMEM columns
@@ -104,6 +114,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+// the leader's barriers also receive arrivals from the peer CTA.  Default (.release/.acquire at .cta scope) semantics
+// as in CUTLASS' ClusterBarrier: a .cluster-scope release costs several hundred cycles per arrival.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local_addr) {     // same offset in the shared memory of cluster rank 0
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local_addr));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -122,13 +159,15 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    // arrives on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs have completed
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
@@ -221,8 +260,6 @@ __device__ __forceinline__ void max32(const uint32_t (&v)[32], float (&m)[4]) {
         m[3] = max3(m[3], __uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
     }
 }
-
-
 // ---- the kernel ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsTc, 1)
 zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t* __restrict__ wimg,
@@ -234,19 +271,23 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
     auto bar = [&](int i) { return sbase + kSmBar + 8u * (uint32_t)i; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int half = blockIdx.x & 1, pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const int T = (N + kTile - 1) / kTile;
+    const int rank = (int)cluster_rank();                 // 0 = leader (issues every MMA of the pair)
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int T = (N + kPairTile - 1) / kPairTile;        // pair-tiles per hypothesis
     const int n_loc = pair < n ? (n - pair + n_pairs - 1) / n_pairs : 0;
     const int total = n_loc * T;
-    const long long total_rows = (long long)n * N;
 
     // ---- one-time setup ------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(bar(BAR_W_FULL), 1);
-        for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_X_FULL + s), 1); mbar_init(bar(BAR_X_EMPTY + s), 1); }
-        mbar_init(bar(BAR_D1_FULL), 1); mbar_init(bar(BAR_A2_FULL), 1); mbar_init(bar(BAR_D2_FULL), 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(bar(BAR_A3_FULL + b), 1); mbar_init(bar(BAR_A3_EMPTY + b), 1); }
-        for (int b = 0; b < kD3Bufs; ++b) { mbar_init(bar(BAR_D3_FULL + b), 1); mbar_init(bar(BAR_D3_EMPTY + b), 1); }
+        mbar_init(bar(BAR_WP_FULL), 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar(BAR_X_FULL + s), 1); mbar_init(bar(BAR_X_EMPTY + s), 1); mbar_init(bar(BAR_XP_FULL + s), 1);
+        }
+        mbar_init(bar(BAR_D1_FULL), 1); mbar_init(bar(BAR_D2_FULL), 1);
+        mbar_init(bar(BAR_A2_FULL), 8);                                   // one arrival per epilogue warp of the pair (4 + 4)
+        for (int b = 0; b < 2; ++b) { mbar_init(bar(BAR_A3_FULL + b), 8); mbar_init(bar(BAR_A3_EMPTY + b), 1); }
+        for (int b = 0; b < kD3Bufs; ++b) { mbar_init(bar(BAR_D3_FULL + b), 1); mbar_init(bar(BAR_D3_EMPTY + b), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // zero the feature stages and the zero block (stale bytes must be finite), stage the small biases
@@ -256,49 +297,80 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
     for (int i = tid; i < 128; i += kThreadsTc) reinterpret_cast<float*>(sm + kSmB2)[i] = wf32[ZS_OFF_B2 + i];
     fence_proxy_async();
     if (warp == 9) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmTmemPtr), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmTmemPtr), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync();                                       // both CTAs: barriers initialised, TMEM allocated
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kSmTmemPtr);
+
+    // No padding rows: a half-tile that would run past the hypothesis' last point is shifted back to end at it
+    // (re-reading points the pair already has -- max-pooling ignores duplicates), and a hypothesis with fewer than
+    // 128 points fills the tile with repeats of itself.  Every accumulator column is then a real point of the right
+    // hypothesis and the max-pool epilogue needs no masking.
+    // First feature row of this CTA's half of pair-tile `tt` of local hypothesis `j` (N >= kTile):
+    auto tile_row0 = [&](int j, int tt) {
+        const int s0 = tt * kPairTile + rank * kTile;
+        return (long long)(pair + j * n_pairs) * N + (long long)(s0 + kTile <= N ? s0 : (N >= kTile ? N - kTile : 0));
+    };
 
     if (warp == 8) {
         // ===== bulk-copy producer =================================================================
         if (lane == 0) {
-            mbar_expect_tx(bar(BAR_W_FULL), 131072 + 16384 + 2048);
+            mbar_expect_tx(bar(BAR_W_FULL), 131072 + 8192 + 1024);
             for (int c = 0; c < 8; ++c)
-                bulk_g2s(sbase + kSmW3 + c * 16384, wimg + (size_t)half * kImgW3Half + (size_t)c * 16384, 16384, bar(BAR_W_FULL));
-            bulk_g2s(sbase + kSmW2, wimg + kImgW2, 16384, bar(BAR_W_FULL));
-            bulk_g2s(sbase + kSmW1, wimg + kImgW1, 2048, bar(BAR_W_FULL));
+                bulk_g2s(sbase + kSmW3 + c * 16384, wimg + (size_t)rank * kImgW3Half + (size_t)c * 16384, 16384, bar(BAR_W_FULL));
+            bulk_g2s(sbase + kSmW2, wimg + kImgW2 + (size_t)rank * 8192, 8192, bar(BAR_W_FULL));
+            bulk_g2s(sbase + kSmW1, wimg + kImgW1 + (size_t)rank * 1024, 1024, bar(BAR_W_FULL));
+            // The leader's issuer must also know that the PEER's operands have landed: the peer's producer
+            // relays its own completions (one tile behind its copies) to barriers in the leader's shared memory.
+            const bool relay = rank != 0;
+            const uint32_t wp = leader_addr(bar(BAR_WP_FULL)), xp = leader_addr(bar(BAR_XP_FULL));
+            if (relay) { mbar_wait(bar(BAR_W_FULL), 0); mbar_arrive_leader(wp); }
             for (int i = 0; i < total; ++i) {
                 const int s = i % kStages, j = i / T, tt = i - j * T;
-                const long long row0 = (long long)(pair + j * n_pairs) * N + (long long)tt * kTile;
-                const long long left = (total_rows - row0) * 16;
-                const uint32_t bytes = left < 2048 ? (uint32_t)left : 2048u;
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(feat) + tile_row0(j, tt) * 16;
                 mbar_wait(bar(BAR_X_EMPTY + s), ((i / kStages) & 1) ^ 1);
-                mbar_expect_tx(bar(BAR_X_FULL + s), bytes);
-                bulk_g2s(sbase + kSmX + s * 2048, reinterpret_cast<const uint8_t*>(feat) + row0 * 16, bytes, bar(BAR_X_FULL + s));
+                mbar_expect_tx(bar(BAR_X_FULL + s), 2048);
+                if (N >= kTile) {
+                    bulk_g2s(sbase + kSmX + s * 2048, src, 2048, bar(BAR_X_FULL + s));
+                } else {
+                    for (int r = 0; r < kTile; r += N)      // the whole (short) hypothesis, repeated
+                        bulk_g2s(sbase + kSmX + s * 2048 + r * 16, src, (uint32_t)min(N, kTile - r) * 16, bar(BAR_X_FULL + s));
+                }
+                if (relay && i >= 1) {
+                    const int ip = i - 1, sp = ip % kStages;
+                    mbar_wait(bar(BAR_X_FULL + sp), (ip / kStages) & 1);
+                    mbar_arrive_leader(xp + 8u * sp);
+                }
+            }
+            if (relay && total >= 1) {
+                const int ip = total - 1, sp = ip % kStages;
+                mbar_wait(bar(BAR_X_FULL + sp), (ip / kStages) & 1);
+                mbar_arrive_leader(xp + 8u * sp);
             }
         }
     } else if (warp == 9) {
-        // ===== MMA issuer (one thread) ============================================================
-        if (elect_one()) {
-            constexpr uint32_t idesc_l1 = make_idesc(128, 64), idesc_128 = make_idesc(128, 128);
+        // ===== MMA issuer (one thread of the leader CTA) ==========================================
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc_l1 = make_idesc(256, 64), idesc_128 = make_idesc(256, 128);
             mbar_wait(bar(BAR_W_FULL), 0);
-            PROF_DECL;
+            mbar_wait_cluster(bar(BAR_WP_FULL), 0);
             tc_fence_after();
+            PROF_DECL;
             // Descriptors differ only in their 14-bit start-address field, so every MMA's pair is "base low word +
             // immediate": the issuing thread must not spend more than ~64 cycles of dependent address arithmetic
             // per MMA or it, not the tensor pipe, paces the kernel (tools/mma_probe.cu measures exactly that).
+            // A descriptor names the same offset in both CTAs' shared memory.
             constexpr uint32_t hi_sw = desc_hi(1024, kLayoutSw128), hi_x = desc_hi(128, kLayoutNone);
             const uint32_t w3_lo = desc_lo(sbase + kSmW3, 16), w2_lo = desc_lo(sbase + kSmW2, 16);
-            const uint32_t w1_lo = desc_lo(sbase + kSmW1, 1024);
-            auto issue_l3 = [&](int it, int cb) {           // layer 3, channel block cb of tile `it`
-                const int q = it * 4 + cb, b = q % kD3Bufs, buf = it & 1;   // A3_FULL of tile `it` was awaited by the caller
-                const uint32_t a3_lo = desc_lo(sbase + kSmA3 + buf * 32768, 16), d3 = tmem + kColD3 + b * 128;
-                PROF_WAIT(1, mbar_wait(bar(BAR_D3_EMPTY + b), ((q / kD3Bufs) & 1) ^ 1));
+            const uint32_t w1_lo = desc_lo(sbase + kSmW1, 512);
+            auto issue_l3 = [&](int it, int cb, int hh) {   // layer 3 of pair-tile `it`: channel block cb, point half hh
+                const int q = it * 8 + cb * 2 + hh, b = q % kD3Bufs, buf = it & 1;   // A3_FULL of `it` was awaited by the caller
+                const uint32_t a3_lo = desc_lo(sbase + kSmA3 + buf * 32768 + hh * 8192, 16), d3 = tmem + kColD3 + b * 128;
+                PROF_WAIT(1, mbar_wait_cluster(bar(BAR_D3_EMPTY + b), ((q / kD3Bufs) & 1) ^ 1));
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -307,47 +379,51 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                            desc_at(a3_lo, hi_sw, kb * 16384 + kk * 32), idesc_128, k > 0);
                 }
                 tc_commit(bar(BAR_D3_FULL + b));
-                if (cb == 3) tc_commit(bar(BAR_A3_EMPTY + buf));
+                if (cb == 3 && hh == 1) tc_commit(bar(BAR_A3_EMPTY + buf));
             };
             for (int i = 0; i <= total; ++i) {
-                // H2 of tile i-1 is ready and D2 (which D1 aliases) has been drained by epilogue 2
-                if (i >= 1) PROF_WAIT(0, mbar_wait(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1));
+                // H2 of pair-tile i-1 is ready in both CTAs and D2 (which D1 aliases) has been drained by both epilogues 2
+                if (i >= 1) PROF_WAIT(0, mbar_wait_cluster(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1));
                 if (i < total) {
                     const int s = i % kStages;
                     PROF_WAIT(3, mbar_wait(bar(BAR_X_FULL + s), (i / kStages) & 1));
+                    PROF_WAIT(3, mbar_wait_cluster(bar(BAR_XP_FULL + s), (i / kStages) & 1));
                     tc_fence_after();
                     const uint32_t xa = sbase + kSmX + s * 2048;
                     tc_mma(tmem + kColD1, desc_at(desc_lo(xa, (sbase + kSmZero) - xa), hi_x, 0), desc_at(w1_lo, hi_x, 0), idesc_l1, 0);
                     tc_commit(bar(BAR_X_EMPTY + s));
                     tc_commit(bar(BAR_D1_FULL));
                 }
-                if (i >= 1) { issue_l3(i - 1, 0); }
+                if (i >= 1) { issue_l3(i - 1, 0, 0); issue_l3(i - 1, 0, 1); }
                 if (i < total) {
                     const uint32_t a2_lo = desc_lo(sbase + kSmA3 + (i & 1) * 32768, 16);
-                    PROF_WAIT(2, mbar_wait(bar(BAR_A2_FULL), i & 1));
+                    PROF_WAIT(2, mbar_wait_cluster(bar(BAR_A2_FULL), i & 1));
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                         tc_mma(tmem + kColD2, desc_at(a2_lo, hi_sw, kk * 32), desc_at(w2_lo, hi_sw, kk * 32), idesc_128, kk > 0);
                     tc_commit(bar(BAR_D2_FULL));
                 }
-                if (i >= 1) { issue_l3(i - 1, 1); issue_l3(i - 1, 2); issue_l3(i - 1, 3); }
+                if (i >= 1) {
+#pragma unroll
+                    for (int cb = 1; cb < 4; ++cb) { issue_l3(i - 1, cb, 0); issue_l3(i - 1, cb, 1); }
+                }
             }
             PROF_DUMP(0, 4);
         }
     } else if (warp < 4) {
         // ===== front epilogues: D1 -> H1 (bf16, swizzled), D2 -> H2 ================================
-        const uint32_t r = (uint32_t)tid;                               // TMEM lane = point row of the tile
+        const uint32_t r = (uint32_t)tid;                               // TMEM lane = point row of this CTA's half-tile
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
         const float* b1 = reinterpret_cast<const float*>(sm + kSmB1);
         const float* b2 = reinterpret_cast<const float*>(sm + kSmB2);
+        const uint32_t a2_full = leader_addr(bar(BAR_A2_FULL)), a3_full = leader_addr(bar(BAR_A3_FULL));
         PROF_DECL;
         for (int i = 0; i < total; ++i) {
             const int buf = i & 1, j = i / T, tt = i - j * T;
-            const long long row0 = (long long)(pair + j * n_pairs) * N + (long long)tt * kTile;
-            const int valid = min(kTile, N - tt * kTile);
+            const long long drow = tile_row0(j, tt) + (N >= kTile ? (int)r : (int)r % N);   // the point this row holds
             uint8_t* a3 = sm + kSmA3 + buf * 32768;
-            PROF_WAIT(0, mbar_wait(bar(BAR_A3_EMPTY + buf), ((i >> 1) & 1) ^ 1));     // layer 3 of tile i-2 has released this buffer
+            PROF_WAIT(0, mbar_wait(bar(BAR_A3_EMPTY + buf), ((i >> 1) & 1) ^ 1));     // layer 3 of pair-tile i-2 has released this buffer
             PROF_WAIT(1, mbar_wait(bar(BAR_D1_FULL), i & 1));
             tc_fence_after();
             {   // layer 1: 64 channels = two 32-column loads in flight, one wait
@@ -357,15 +433,15 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 tc_wait_ld();
                 epi_store32(v0, b1, a3, r, 0);
                 epi_store32(v1, b1 + 32, a3, r, 4);
-                if (kDbgDump && dbg_h1 && half == 0 && (int)r < valid) {
-                    dbg_dump32(dbg_h1 + (row0 + r) * 64, v0, b1);
-                    dbg_dump32(dbg_h1 + (row0 + r) * 64 + 32, v1, b1 + 32);
+                if (kDbgDump && dbg_h1) {
+                    dbg_dump32(dbg_h1 + drow * 64, v0, b1);
+                    dbg_dump32(dbg_h1 + drow * 64 + 32, v1, b1 + 32);
                 }
             }
             fence_proxy_async();
             tc_fence_before();
-            named_bar(1, 128);
-            if (tid == 0) mbar_arrive(bar(BAR_A2_FULL));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(a2_full);
 
             PROF_WAIT(2, mbar_wait(bar(BAR_D2_FULL), i & 1));
             tc_fence_after();
@@ -377,74 +453,71 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 tc_wait_ld();
                 epi_store32(v0, b2 + kb * 64, a3 + kb * 16384, r, 0);
                 epi_store32(v1, b2 + kb * 64 + 32, a3 + kb * 16384, r, 4);
-                if (kDbgDump && dbg_h2 && half == 0 && (int)r < valid) {
-                    dbg_dump32(dbg_h2 + (row0 + r) * 128 + kb * 64, v0, b2 + kb * 64);
-                    dbg_dump32(dbg_h2 + (row0 + r) * 128 + kb * 64 + 32, v1, b2 + kb * 64 + 32);
+                if (kDbgDump && dbg_h2) {
+                    dbg_dump32(dbg_h2 + drow * 128 + kb * 64, v0, b2 + kb * 64);
+                    dbg_dump32(dbg_h2 + drow * 128 + kb * 64 + 32, v1, b2 + kb * 64 + 32);
                 }
             }
             fence_proxy_async();
             tc_fence_before();
-            named_bar(1, 128);
-            if (tid == 0) mbar_arrive(bar(BAR_A3_FULL + buf));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(a3_full + 8u * buf);
         }
         if (tid == 0) PROF_DUMP(8, 3);
     } else {
         // ===== max-pool epilogue: D3[channel lane][point column] -> running max -> pooled ===========
+        // Columns of a layer-3 accumulator of point half hh: 0-63 = points 64*hh.. of the leader's half-tile,
+        // 64-127 = points 64*hh.. of the peer's half-tile (the N side concatenates the two CTAs' operand rows).
+        // Every column is a real point (see tile_row0), so this is a plain max.  The point-half loop is kept
+        // rolled: eight unrolled copies of the body overflow the instruction cache.
         const int wq = warp - 4;                                        // TMEM lane quadrant == warp % 4
         const int L = wq * 32 + lane;                                   // channel within the 128-channel block
         const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
+        const uint32_t d3_empty = leader_addr(bar(BAR_D3_EMPTY));
         float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         PROF_DECL;
         for (int i = 0; i < total; ++i) {
             const int j = i / T, tt = i - j * T;
             const int h = pair + j * n_pairs;
-            const int valid = min(kTile, N - tt * kTile);
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
-                const int q = i * 4 + cb, b = q % kD3Bufs;
-                PROF_WAIT(0, mbar_wait(bar(BAR_D3_FULL + b), (q / kD3Bufs) & 1));
-                tc_fence_after();
-                float mm = m[cb];
-                {
-                    uint32_t v0[32], v1[32], v2[32], v3[32];           // all 128 point columns in flight, one wait
-                    const uint32_t a = lane_addr + kColD3 + b * 128;
-                    if (!EXP(4)) { tc_ld32(a, v0); tc_ld32(a + 32, v1); tc_ld32(a + 64, v2); tc_ld32(a + 96, v3); }
-                    tc_wait_ld();
-                    if (valid == kTile) {
-                        float q[4] = {mm, -INFINITY, -INFINITY, -INFINITY};
-                        max32(v0, q); max32(v1, q); max32(v2, q); max32(v3, q);
-                        mm = fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3]));
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            if (c < valid) mm = fmaxf(mm, __uint_as_float(v0[c]));
-                            if (32 + c < valid) mm = fmaxf(mm, __uint_as_float(v1[c]));
-                            if (64 + c < valid) mm = fmaxf(mm, __uint_as_float(v2[c]));
-                            if (96 + c < valid) mm = fmaxf(mm, __uint_as_float(v3[c]));
-                        }
+                float qq[4] = {m[cb], -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int q = i * 8 + cb * 2 + hh, b = q % kD3Bufs;
+                    PROF_WAIT(0, mbar_wait(bar(BAR_D3_FULL + b), (q / kD3Bufs) & 1));
+                    tc_fence_after();
+                    {
+                        uint32_t v0[32], v1[32], v2[32], v3[32];           // all 128 point columns in flight, one wait
+                        const uint32_t a = lane_addr + kColD3 + b * 128;
+                        PROF_WAIT(1, if (!EXP(4)) { tc_ld32(a, v0); tc_ld32(a + 32, v1); tc_ld32(a + 64, v2); tc_ld32(a + 96, v3); }
+                                     tc_wait_ld());
+                        max32(v0, qq); max32(v1, qq); max32(v2, qq); max32(v3, qq);
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    PROF_WAIT(3, if (lane == 0) mbar_arrive_leader(d3_empty + 8u * b));
                 }
-                tc_fence_before();
-                named_bar(2, 128);
-                if (tid == 128) mbar_arrive(bar(BAR_D3_EMPTY + b));
+                float mm = fmaxf(fmaxf(qq[0], qq[1]), fmaxf(qq[2], qq[3]));
                 if (tt == T - 1) {
-                    const int ch = half * 512 + cb * 128 + L;
+                    const int ch = rank * 512 + cb * 128 + L;
                     pooled[(size_t)h * 1024 + ch] = fmaxf(mm + __ldg(wf32 + ZS_OFF_B3 + ch), 0.f);
                     mm = -INFINITY;
                 }
                 m[cb] = mm;
             }
         }
-        if (tid == 128) PROF_DUMP(16, 1);
+        if (tid == 128) PROF_DUMP(16, 4);
     }
 
     // ---- teardown --------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    cluster_sync();                        // the peer may still be signalling this CTA's barriers / reading its operands
     if (warp == 9) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -459,15 +532,16 @@ __global__ void zs_k_build_images(const float* __restrict__ w, uint8_t* __restri
         const size_t off = (size_t)half * kImgW3Half + (size_t)(cb * 2 + kb) * 16384 + sw128_off(mrow, kc >> 3) + (kc & 7) * 2;
         *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(w[ZS_OFF_W3 + i]);
     }
-    // W2: 128 x 64
+    // W2: 128 x 64; rows 0-63 (leader's share of the N side) and 64-127 (peer's) are the two 8 KB halves of the image
     if (i < 128 * 64) {
         const int ch = i >> 6, k = i & 63;
         *reinterpret_cast<__nv_bfloat16*>(img + kImgW2 + sw128_off(ch, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(w[ZS_OFF_W2 + i]);
     }
-    // W1: 64 x 16 (K 8..15 zero), no swizzle: chunk-major core matrices
+    // W1: 64 x 16 (K 8..15 zero), no swizzle, chunk-major core matrices; rows 0-31 (leader's share of the N side)
+    // and rows 32-63 (peer's) are separate 1 KB images
     if (i < 64 * 16) {
-        const int ch = i >> 4, k = i & 15;
-        const size_t off = (size_t)(k >> 3) * 1024 + (size_t)(ch >> 3) * 128 + (ch & 7) * 16 + (k & 7) * 2;
+        const int ch = i >> 4, k = i & 15, chl = ch & 31;
+        const size_t off = (size_t)(ch >> 5) * 1024 + (size_t)(k >> 3) * 512 + (size_t)(chl >> 3) * 128 + (chl & 7) * 16 + (k & 7) * 2;
         const float v = k < 8 ? w[ZS_OFF_W1 + ch * 8 + k] : 0.f;
         *reinterpret_cast<__nv_bfloat16*>(img + kImgW1 + off) = __float2bfloat16_rn(v);
     }
@@ -497,8 +571,20 @@ static int launch_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, in
 #endif
     int grid = ctx->sm_count & ~1;                 // CTA pairs
     if (grid > 2 * n) grid = 2 * n;
-    zs_k_mlp_tc<<<grid, kThreadsTc, kSmAlloc, st>>>(feat, n, n_pts, reinterpret_cast<const uint8_t*>(w.bf16), w.f32,
-                                                     pooled, dbg_h1, dbg_h2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(kThreadsTc, 1, 1);
+    cfg.dynamicSmemBytes = kSmAlloc;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;    // CTA pair = the two SMs of a TPC (cta_group::2 MMAs)
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ZS_CUDA(ctx, cudaLaunchKernelEx(&cfg, zs_k_mlp_tc, feat, n, n_pts, reinterpret_cast<const uint8_t*>(w.bf16),
+                                    (const float*)w.f32, pooled, dbg_h1, dbg_h2));
     ZS_LAUNCHED(ctx);
     return ZS_OK;
 }

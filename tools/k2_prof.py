@@ -19,10 +19,13 @@ for _ in range(2):
 torch.cuda.synchronize()
 n_cta = 148
 p = h2.reshape(-1)[: n_cta * 24 * 2].view(torch.int64).reshape(n_cta, 24).cpu().double()
-tiles = n / (n_cta // 2) * -(-N // 128)
+tiles = n / (n_cta // 2) * -(-N // 256)   # pair-tiles (256 points) per CTA
 rows = [("issuer total", 0), ("issuer wait a3_full (H2 ready)", 1), ("issuer wait d3_empty", 2), ("issuer wait a2_full (H1 ready)", 3),
         ("issuer wait x_full", 4), ("front total", 8), ("front wait a3_empty", 9), ("front wait d1_full", 10),
-        ("front wait d2_full", 11), ("maxpool total", 16), ("maxpool wait d3_full", 17)]
+        ("front wait d2_full", 11), ("maxpool total", 16), ("maxpool wait d3_full", 17), ("maxpool tmem load + wait::ld", 18),
+        ("maxpool fence + named barrier", 19), ("maxpool arrive d3_empty", 20)]
 print(f"n={n} N={N} tiles per CTA {tiles:.0f}")
 for nm, i in rows:
-    print(f"{nm:34s} {p[:, i].mean().item() / tiles:9.0f} cycles/tile")
+    col = p[:, i]
+    col = col[col > 0] if i < 8 else col          # issuer counters exist in leader CTAs only
+    print(f"{nm:34s} {col.mean().item() / tiles:9.0f} cycles/pair-tile")
