@@ -289,7 +289,13 @@ def main():
         peak = peaks["tensor_sustained"]
         roof["roofline"] = {"kernel": "zs_pool (shared MLP 8-64-128-1024 + max-pool)", "bound": "tensor",
                             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                            "peak_source": peaks["source"] + ", sustained bf16", "launch_groups": st["calls"],
+                            "peak_source": peaks["source"] + ", sustained bf16 (cuBLAS 8192^3 back to back)",
+                            "peak_burst": peaks["tensor_burst"], "frac_of_burst": ach / peaks["tensor_burst"],
+                            "peak_nominal_dense": 2250.0, "frac_of_nominal": ach / 2250.0,
+                            "note": "a fraction above 1 means this kernel sustains more than the measured cuBLAS GEMM does: "
+                                    "both are power-limited, and the fused MLP moves fewer operand bytes per MAC "
+                                    "(weights resident in shared memory, activations never leave the SM)",
+                            "launch_groups": st["calls"],
                             "ms_in_timed_region": st["ms"], "share_of_step": st["ms"] / (ms_step * args.steps)}
     if "features" in stages:
         st = stages["features"]
@@ -309,6 +315,8 @@ def main():
     reps = max(1, -(-32768 // max(r0["poses12"].shape[0], 1)))
     p_big = r0["poses12"].repeat(reps, 1)[:32768].contiguous()
     buf = torch.empty((p_big.shape[0], n_pts, 8), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize(dev)
+    time.sleep(2.0)      # "standalone": let the clocks recover from the power-capped tensor-core phase above
     for _ in range(3):
         fs.ctx.features(r0["slot"], p_big, out=buf)
     torch.cuda.synchronize(dev)

@@ -88,6 +88,10 @@ enum : int {
 // A3_FULL of this tile (epilogue 2 has drained D2).  That leaves room for THREE layer-3 accumulators.
 constexpr uint32_t kColD1 = 0, kColD2 = 0, kColD3 = 128;
 constexpr int kD3Bufs = 3;
+#ifndef ZS_L2_AFTER
+#define ZS_L2_AFTER 1
+#endif
+constexpr int kL2After = ZS_L2_AFTER;     // layer 2 of pair-tile i is issued behind this many channel blocks of layer 3 of pair-tile i-1
 constexpr uint32_t kTmemCols = 512;
 
 // global image of the bf16 operands (bytes): W3 half 0, W3 half 1, W2, W1
@@ -394,7 +398,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                     tc_commit(bar(BAR_X_EMPTY + s));
                     tc_commit(bar(BAR_D1_FULL));
                 }
-                if (i >= 1) { issue_l3(i - 1, 0, 0); issue_l3(i - 1, 0, 1); }
+                if (i >= 1) { issue_l3(i - 1, 0, 0); issue_l3(i - 1, 0, 1); if (kL2After >= 2) { issue_l3(i - 1, 1, 0); issue_l3(i - 1, 1, 1); } }
                 if (i < total) {
                     const uint32_t a2_lo = desc_lo(sbase + kSmA3 + (i & 1) * 32768, 16);
                     PROF_WAIT(2, mbar_wait_cluster(bar(BAR_A2_FULL), i & 1));
@@ -406,7 +410,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 }
                 if (i >= 1) {
 #pragma unroll
-                    for (int cb = 1; cb < 4; ++cb) { issue_l3(i - 1, cb, 0); issue_l3(i - 1, cb, 1); }
+                    for (int cb = kL2After; cb < 4; ++cb) { issue_l3(i - 1, cb, 0); issue_l3(i - 1, cb, 1); }
                 }
             }
             PROF_DUMP(0, 4);
@@ -492,11 +496,12 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                         const uint32_t a = lane_addr + kColD3 + b * 128;
                         PROF_WAIT(1, if (!EXP(4)) { tc_ld32(a, v0); tc_ld32(a + 32, v1); tc_ld32(a + 64, v2); tc_ld32(a + 96, v3); }
                                      tc_wait_ld());
+                        // the accumulator is free as soon as it sits in registers: release it before the arithmetic
+                        tc_fence_before();
+                        __syncwarp();
+                        PROF_WAIT(3, if (lane == 0) mbar_arrive_leader(d3_empty + 8u * b));
                         max32(v0, qq); max32(v1, qq); max32(v2, qq); max32(v3, qq);
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    PROF_WAIT(3, if (lane == 0) mbar_arrive_leader(d3_empty + 8u * b));
                 }
                 float mm = fmaxf(fmaxf(qq[0], qq[1]), fmaxf(qq[2], qq[3]));
                 if (tt == T - 1) {

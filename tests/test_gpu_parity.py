@@ -300,7 +300,8 @@ def _oracle_layers_bf16(x_bf16, w):
     return h1, h2, h3.max(dim=1).values
 
 
-@pytest.mark.parametrize("n,N", [(1, 128), (2, 256), (3, 100), (5, 1000), (150, 130), (1, 1), (40, 1000)])
+@pytest.mark.parametrize("n,N", [(1, 128), (2, 256), (3, 100), (5, 1000), (150, 130), (1, 1), (40, 1000),
+                                 (7, 300), (3, 4000), (149, 257), (2, 127), (5, 384)])
 def test_tc_scorer_layers_match_bf16_oracle(ctx, n, N):
     """tcgen05 path layer by layer vs the bf16-emulating oracle (tight), then end scores vs fp32 oracle (1e-2)."""
     g = torch.Generator().manual_seed(7 * n + N)
