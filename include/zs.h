@@ -156,6 +156,12 @@ ZS_API int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat_bf16, in
 ZS_API int zs_topk(zs_ctx* ctx, const float* scores, int n, int k, int index_base, const int32_t* index_map,
             float* s_out, int32_t* i_out, void* stream);
 
+/* The same for all objects of a frame in one launch (one CTA per object).  segments [dev] int32 [n_segments][4] =
+ * {first score, count, index_base, 0}; scores [dev] and index_map [dev] (nullable) are indexed by first score + i.
+ * s_out [dev] float32 [n_segments][k], i_out [dev] int32 [n_segments][k]. */
+ZS_API int zs_topk_segments(zs_ctx* ctx, const float* scores, const int32_t* segments, int n_segments, int k,
+                     const int32_t* index_map, float* s_out, int32_t* i_out, void* stream);
+
 /* Batched ADD / ADI pose error of every hypothesis against one ground-truth pose; replaces the Python loop
  * `[err_func(R, t, R_gt, t_gt, model_points) for mat in poses_all]` (online_learning.py:452, err_func = add | adi
  * from zephyr.utils.metrics, :32,337-339).  gt_pose [dev] float32 [12] (R|t rows), pts [dev] float32 (n_pts,3),

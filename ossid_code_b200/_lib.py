@@ -36,6 +36,7 @@ SIGNATURES = {
     "zs_pool_debug": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p]),
     "zs_pose_errors": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _p]),
     "zs_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "zs_topk_segments": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -15,9 +15,20 @@ __device__ __forceinline__ uint32_t f2key(float f) {
 
 // Selection by k passes of a block-wide arg-max over keys strictly below the previous winner.
 // key = (f2key(score) << 32) | (0xffffffff - index): unique per element, max = best.
+// One CTA per segment (object): segment g covers scores[seg[4g] .. seg[4g]+seg[4g+1]), reports index + seg[4g+2].
+// seg == nullptr: a single segment [0, n) with index_base (the zs_topk entry point).
 __global__ void __launch_bounds__(1024)
 zs_k_topk(const float* __restrict__ scores, int n, int k, int index_base, const int32_t* __restrict__ index_map,
-          float* __restrict__ s_out, int32_t* __restrict__ i_out) {
+          const int32_t* __restrict__ seg, float* __restrict__ s_out, int32_t* __restrict__ i_out) {
+    if (seg) {
+        const int32_t* e = seg + 4 * blockIdx.x;
+        scores += e[0];
+        if (index_map) index_map += e[0];
+        n = e[1];
+        index_base = e[2];
+        s_out += (size_t)blockIdx.x * k;
+        i_out += (size_t)blockIdx.x * k;
+    }
     __shared__ unsigned long long s_best[32];
     __shared__ unsigned long long s_prev;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -66,7 +77,19 @@ extern "C" int zs_topk(zs_ctx* ctx, const float* scores, int n, int k, int index
     if (n < 0 || k <= 0 || k > ZS_MAX_TOPK || !s_out || !i_out || (n > 0 && !scores))
         return zs_fail(ctx, ZS_ERR_INVALID, "zs_topk n %d k %d", n, k);
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
-    zs_k_topk<<<1, 1024, 0, (cudaStream_t)stream>>>(scores, n, k, index_base, index_map, s_out, i_out);
+    zs_k_topk<<<1, 1024, 0, (cudaStream_t)stream>>>(scores, n, k, index_base, index_map, nullptr, s_out, i_out);
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
+extern "C" int zs_topk_segments(zs_ctx* ctx, const float* scores, const int32_t* segments, int n_segments, int k,
+                                const int32_t* index_map, float* s_out, int32_t* i_out, void* stream) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (n_segments == 0) return ZS_OK;
+    if (n_segments < 0 || k <= 0 || k > ZS_MAX_TOPK || !s_out || !i_out || !segments)
+        return zs_fail(ctx, ZS_ERR_INVALID, "zs_topk_segments n_segments %d k %d", n_segments, k);
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    zs_k_topk<<<n_segments, 1024, 0, (cudaStream_t)stream>>>(scores, 0, k, 0, index_map, segments, s_out, i_out);
     ZS_LAUNCHED(ctx);
     return ZS_OK;
 }

@@ -248,6 +248,17 @@ class ZsContext:
                                   s.data_ptr(), i.data_ptr(), self._stream()), "zs_topk")
         return s, i
 
+    def topk_segments(self, scores: torch.Tensor, segments: torch.Tensor, k: int, index_map: Optional[torch.Tensor] = None):
+        """Per-segment top-k in one launch.  ``segments``: int32 (n_seg,4) device tensor of {first, count, index_base, 0}.
+        Returns (n_seg,k) scores and indices (index = index_map[first+i] (if given) + index_base)."""
+        n_seg = segments.shape[0]
+        s = torch.empty((n_seg, k), dtype=torch.float32, device=self.device)
+        i = torch.empty((n_seg, k), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.zs_topk_segments(self.h, scores.data_ptr() if scores.numel() else None, segments.data_ptr(), n_seg, k,
+                                           index_map.data_ptr() if index_map is not None and index_map.numel() else None,
+                                           s.data_ptr(), i.data_ptr(), self._stream()), "zs_topk_segments")
+        return s, i
+
 
 _contexts = {}
 

@@ -108,6 +108,7 @@ class FrameScorer:
         self._pooled = None
         self._scores = None
         self._resident = None
+        self._segments = None
         self.forced_rank_world = None
         self.stage_events = None     # set to [] to record (stage, units, start_event, end_event) per launch group
 
@@ -169,6 +170,7 @@ class FrameScorer:
             poses12 = poses_to_rt12(torch.as_tensor(ob["pose_hypos"])[lo:hi], ctx.device)
             res.append(dict(slot=slot, poses12=poses12, lo=lo, M=M, wslot=weight_of(o) % max(self.n_weights, 1)))
         self._resident = res
+        self._segments = None
         return res
 
     # -- compute (everything resident) --------------------------------------------------
@@ -223,13 +225,21 @@ class FrameScorer:
                 t = self._mark("head", hi - lo)
                 ctx.head(ws, self._pooled[lo:hi], tensor_cores, out=self._scores[lo:hi])
                 self._mark(None, 0, t)
-        # 5. per-object top-k; indices mapped back to global hypothesis indices inside the kernel
-        top_s, top_i = [], []
-        for o, r in enumerate(res):
-            ts, ti = ctx.topk(self._scores[offs[o]: offs[o] + n_keeps[o]], k, r["lo"], index_map=keeps[o])
-            top_s.append(ts)
-            top_i.append(ti)
-        S, I = torch.stack(top_s), torch.stack(top_i)
+        # 5. per-object top-k in one launch (one CTA per object); indices mapped back to global hypothesis indices
+        #    inside the kernel.  The segment table only depends on the uploaded frame, so it is built once per upload
+        #    when no pre-filter is active (kept counts are then known on the host without a read-back).
+        if all(kp is None for kp in keeps):
+            if self._segments is None:
+                self._segments = torch.tensor([[offs[o], n_keeps[o], r["lo"], 0] for o, r in enumerate(res)],
+                                              dtype=torch.int32).pin_memory().to(ctx.device, non_blocking=True)
+            S, I = ctx.topk_segments(self._scores, self._segments, k)
+        else:
+            top_s, top_i = [], []
+            for o, r in enumerate(res):
+                ts, ti = ctx.topk(self._scores[offs[o]: offs[o] + n_keeps[o]], k, r["lo"], index_map=keeps[o])
+                top_s.append(ts)
+                top_i.append(ti)
+            S, I = torch.stack(top_s), torch.stack(top_i)
         rank, world = self._rank_world()
         if world > 1 and self.forced_rank_world is None:
             S, I = allgather_topk(S, I, k, self.group)

@@ -47,6 +47,46 @@ def test_topk_index_map(ctx):
     assert ti.tolist() == [1020, 1030, 1010] and ts.tolist() == [3.0, 3.0, 0.5]
 
 
+def test_topk_segments_matches_per_object_topk(ctx):
+    """One launch over all objects == zs_topk object by object: ties, an empty segment, a segment shorter than k."""
+    g = torch.Generator().manual_seed(5)
+    counts = [1000, 0, 3, 4097, 64]
+    scores = torch.randn(sum(counts), generator=g)
+    scores[10] = scores[500] = scores[999] = 9.0                 # ties inside segment 0: lowest index first
+    keep = torch.randperm(sum(counts), generator=g).to(torch.int32)
+    seg, first = [], 0
+    for o, c in enumerate(counts):
+        seg.append([first, c, 1000 * o, 0])
+        first += c
+    dev_s, dev_k = scores.to(ctx.device), keep.to(ctx.device)
+    seg_t = torch.tensor(seg, dtype=torch.int32, device=ctx.device)
+    for index_map in (None, dev_k):
+        S, I = ctx.topk_segments(dev_s, seg_t, 8, index_map=index_map)
+        for o, (f, c, base, _) in enumerate(seg):
+            es, ei = ctx.topk(dev_s[f:f + c], 8, base, index_map=None if index_map is None else index_map[f:f + c])
+            assert torch.equal(S[o], es) and torch.equal(I[o], ei), (o, S[o], es, I[o], ei)
+    assert I[1].tolist() == [-1] * 8 and I[2][3:].tolist() == [-1] * 5
+    S0, I0 = ctx.topk_segments(dev_s, seg_t, 8)
+    assert I0[0][:3].tolist() == [10, 500, 999]
+
+
+def test_score_frames_stream_equals_frame_by_frame(ctx):
+    """BASELINE.json config 5 (multi-frame stream between finetune steps): the pipelined score_frames() over different
+    frames returns exactly what score_frame() returns for each frame alone."""
+    frames = []
+    for seed in (3, 4, 5, 6):
+        sc = syn.make_scene(seed, "lmo", n_obj=2, n_pts=384, n_hypo=300)
+        frames.append(dict(img=sc["img"], depth=sc["depth"], cam_K=sc["cam_K"], objects=sc["objects"]))
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    fs = scoring.FrameScorer(ws, device=0, precision="bf16", inconst_ratio_th=100.0, k=4)
+    stream = fs.score_frames(frames, weight_of=lambda o: o % 2, depth=2)
+    assert len(stream) == len(frames)
+    for fr, (S, I) in zip(frames, stream):
+        S1, I1 = fs.score_frame(fr["img"], fr["depth"], fr["cam_K"], fr["objects"], weight_of=lambda o: o % 2)
+        assert np.array_equal(I, I1) and np.array_equal(S, S1)
+    assert len({tuple(I[:, 0].tolist()) + tuple(S[:, 0].tolist()) for S, I in stream}) > 1, "frames should differ"
+
+
 @pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("bf16", 1e-2)])
 def test_frame_scorer_batched_objects_two_scorers(ctx, precision, rtol):
     """3 objects, 2 scorers keyed on object parity (online_learning.py:461-463), pre-filter on: per-object
