@@ -169,6 +169,25 @@ ZS_API int zs_topk_segments(zs_ctx* ctx, const float* scores, const int32_t* seg
 ZS_API int zs_pose_errors(zs_ctx* ctx, const float* poses, int n, const float* gt_pose, const float* pts, int n_pts,
                    int symmetric, float* err_out, void* stream);
 
+/* Batched point-to-point ICP of n poses against the depth image; replaces
+ * `icpRefinement(depth, uv_original[pred_idx], pred_pose, cam_K, model_points, inpaint_depth=False, icp_max_dist=0.01)`
+ * (online_learning.py:476-479; zephyr.utils.icp, which runs Open3D's registration_icp on the CPU for the single
+ * winning pose).  Target cloud = depth back-projected at the pixels uv [dev] int32 ([n][n_src][2] when uv_per_pose != 0,
+ * else one [n_src][2] shared by all poses; [..,0]=x/col, [..,1]=y/row; pixels outside the image or without depth are
+ * ignored); source = src_pts [dev] float32 (n_src,3) under each pose.  depth [dev] float32 H*W metres with intrinsics
+ * fx..cy, or NULL = the context's resident frame (zs_set_frame*; H, W and intrinsics arguments are then ignored).
+ * Open3D's loop and default stopping rule (relative fitness / rmse 1e-6).  poses_out [dev] float32 [n][12];
+ * stats_out [dev] float32 [n][4] = {fitness, inlier_rmse, iterations, correspondences} (nullable). */
+ZS_API int zs_icp_refine(zs_ctx* ctx, const float* poses, int n, const float* src_pts, int n_src, const int32_t* uv,
+                  int uv_per_pose, const float* depth, int H, int W, float fx, float fy, float cx, float cy,
+                  float max_dist, int max_iter, float* poses_out, float* stats_out, void* stream);
+
+/* `estimate_visib_mask_gt(depth, pred_depth, 15/1000.)` (online_learning.py:500; bop_toolkit_lib.visibility):
+ * bop19 rule  visible = (d_model - d_test <= delta || d_test == 0) && d_model > 0;  bop18 != 0 selects
+ * (d_model - d_test <= delta) && d_test > 0 && d_model > 0.  d_test, d_model [dev] float32 [n]; mask_out [dev] uint8 [n]. */
+ZS_API int zs_visib_mask(zs_ctx* ctx, const float* d_test, const float* d_model, size_t n, float delta, int bop18,
+                  uint8_t* mask_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,8 @@ SIGNATURES = {
     "zs_pose_errors": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _p]),
     "zs_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "zs_topk_segments": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "zs_icp_refine": (_i, [_p, _p, _i, _p, _i, _p, _i, _p, _i, _i, _f, _f, _f, _f, _f, _i, _p, _p, _p]),
+    "zs_visib_mask": (_i, [_p, _p, _p, C.c_size_t, _f, _i, _p, _p]),
 }
 
 _lib = None

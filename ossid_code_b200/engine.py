@@ -248,6 +248,46 @@ class ZsContext:
                                   s.data_ptr(), i.data_ptr(), self._stream()), "zs_topk")
         return s, i
 
+    def icp_refine(self, poses12: torch.Tensor, src_pts, uv: torch.Tensor, depth=None, meta=None, max_dist: float = 0.01,
+                   max_iter: int = 30):
+        """Point-to-point ICP of every pose against the depth image (``depth`` None = the resident frame).
+
+        ``uv``: int32 (n_src,2) shared by all poses or (n,n_src,2) per pose.  Returns (poses (n,12) float32,
+        stats (n,4) = fitness, inlier_rmse, iterations, correspondences)."""
+        src = _dev_f32(src_pts, self.device)
+        uv = torch.as_tensor(uv).to(device=self.device, dtype=torch.int32).contiguous()
+        n, n_src = poses12.shape[0], src.shape[0]
+        per_pose = uv.dim() == 3
+        if uv.shape[-2:] != (n_src, 2) or (per_pose and uv.shape[0] != n):
+            raise ValueError(f"uv shape {tuple(uv.shape)} does not match {n} poses x {n_src} points")
+        out = torch.empty((n, 12), dtype=torch.float32, device=self.device)
+        stats = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+        H = W = 0
+        fx = fy = cx = cy = 0.0
+        dptr = None
+        if depth is not None:
+            d = _dev_f32(depth, self.device)
+            H, W = d.shape
+            fx, fy, cx, cy = (float(meta[k]) for k in ("camera_fx", "camera_fy", "camera_cx", "camera_cy"))
+            scale = float(meta.get("camera_scale", 1.0))
+            if scale != 1.0:
+                d = d / scale
+            dptr = d.data_ptr()
+        self._ck(self.lib.zs_icp_refine(self.h, poses12.data_ptr() if n else None, n, src.data_ptr(), n_src, uv.data_ptr(),
+                                        int(per_pose), dptr, H, W, fx, fy, cx, cy, float(max_dist), int(max_iter),
+                                        out.data_ptr(), stats.data_ptr(), self._stream()), "zs_icp_refine")
+        return out, stats
+
+    def visib_mask(self, d_test, d_model, delta: float, bop18: bool = False) -> torch.Tensor:
+        """bop_toolkit visibility rule, elementwise -> bool tensor of d_test's shape."""
+        a, b = _dev_f32(d_test, self.device), _dev_f32(d_model, self.device)
+        if a.shape != b.shape:
+            raise ValueError("d_test and d_model must have the same shape")
+        out = torch.empty(a.shape, dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.zs_visib_mask(self.h, a.data_ptr(), b.data_ptr(), a.numel(), float(delta), int(bool(bop18)),
+                                        out.data_ptr(), self._stream()), "zs_visib_mask")
+        return out.to(torch.bool)
+
     def topk_segments(self, scores: torch.Tensor, segments: torch.Tensor, k: int, index_map: Optional[torch.Tensor] = None):
         """Per-segment top-k in one launch.  ``segments``: int32 (n_seg,4) device tensor of {first, count, index_base, 0}.
         Returns (n_seg,k) scores and indices (index = index_map[first+i] (if given) + index_base)."""

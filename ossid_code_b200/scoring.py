@@ -245,6 +245,34 @@ class FrameScorer:
             S, I = allgather_topk(S, I, k, self.group)
         return S, I
 
+    # -- post-scoring refinement (online_learning.py:471-479) ----------------------------------
+    def refine_winners(self, objects: List[dict], I, n_refine: int = 1, icp_max_dist: float = 0.01, max_iter: int = 30):
+        """ICP-refine the ``n_refine`` best hypotheses of every object of the uploaded frame in one launch per object.
+
+        ``objects``: the list given to ``upload`` (host ``pose_hypos``); ``I``: (n_obj,k) global winner indices from
+        ``run_resident`` (entries < 0 are skipped).  Target cloud = the resident depth at ``uv_original`` of each winner,
+        as the reference passes ``uv_original[pred_idx]`` (online_learning.py:476-479).  Returns
+        ``(poses (n_obj,n_refine,4,4) float64, stats (n_obj,n_refine,4) float32)`` numpy; skipped slots keep identity / zeros.
+        """
+        ctx = self.ctx
+        I = np.asarray(I.cpu() if torch.is_tensor(I) else I)
+        n_obj = len(objects)
+        poses = np.tile(np.eye(4), (n_obj, n_refine, 1, 1))
+        stats = np.zeros((n_obj, n_refine, 4), np.float32)
+        pending = []
+        for o, (ob, r) in enumerate(zip(objects, self._resident)):
+            idx = [int(i) for i in I[o, :n_refine] if i >= 0]
+            if not idx:
+                continue
+            p12 = poses_to_rt12(torch.as_tensor(np.asarray(ob["pose_hypos"])[idx]), ctx.device)
+            _, uv, _, _ = ctx.features(r["slot"], p12, dtype=self.dtype, want_uv=True)
+            out, st = ctx.icp_refine(p12, ob["_zs_host"][0], uv, max_dist=icp_max_dist, max_iter=max_iter)
+            pending.append((o, len(idx), out, st))
+        for o, m, out, st in pending:                       # read back after every object's launches are queued
+            poses[o, :m, :3, :] = out.cpu().numpy().astype(np.float64).reshape(m, 3, 4)
+            stats[o, :m] = st.cpu().numpy()
+        return poses, stats
+
     # -- public end-to-end call -------------------------------------------------------------
     def score_frame(self, img_u8, depth, cam_K, objects: List[dict], weight_of=lambda o: 0):
         """Host buffers in, host results out: ``(scores (n_obj,k), indices (n_obj,k))`` numpy arrays."""

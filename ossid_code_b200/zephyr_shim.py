@@ -140,7 +140,8 @@ def projectPointsUv(pose_hypos, model_points, meta_data, device=0):
 
 
 def install():
-    """Register ``zephyr``, ``zephyr.utils``, ``zephyr.datasets.score_dataset``, ``zephyr.models.pointnet2``."""
+    """Register ``zephyr``, ``zephyr.utils`` (+ ``.metrics``, ``.icp``), ``zephyr.datasets.score_dataset``,
+    ``zephyr.models.pointnet2`` -- the symbols online_learning.py:28-36 imports that this build provides."""
     def mod(name):
         m = sys.modules.get(name)
         if m is None:
@@ -151,7 +152,14 @@ def install():
     z, zu = mod("zephyr"), mod("zephyr.utils")
     zd, zds = mod("zephyr.datasets"), mod("zephyr.datasets.score_dataset")
     zm, zmp = mod("zephyr.models"), mod("zephyr.models.pointnet2")
+    from . import icp as _icp, metrics as _metrics
+    from .zephyr_utils import K2meta
     zu.projectPointsUv = projectPointsUv
+    zu.K2meta = K2meta
+    zum, zui = mod("zephyr.utils.metrics"), mod("zephyr.utils.icp")
+    zum.add, zum.adi = _metrics.add, _metrics.adi                  # online_learning.py:32
+    zui.icpRefinement = _icp.icpRefinement                         # online_learning.py:36
+    zu.metrics, zu.icp = zum, zui
     zds.ScoreDataset = ScoreDataset
     zmp.PointNet2SSG = PointNet2SSG
     z.utils, z.datasets, z.models = zu, zd, zm
