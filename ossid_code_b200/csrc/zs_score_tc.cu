@@ -118,17 +118,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-// the leader's barriers also receive arrivals from the peer CTA.  Default (.release/.acquire at .cta scope) semantics
-// as in CUTLASS' ClusterBarrier: a .cluster-scope release costs several hundred cycles per arrival.
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
+// The leader's barriers also receive arrivals from the peer CTA.  Waits and arrives keep the default (.acquire /
+// .release at .cta scope) semantics, as CUTLASS' ClusterBarrier does for its 2-SM pipelines: an explicit
+// .release.cluster arrive cost several hundred cycles per arrival here.
 __device__ __forceinline__ uint32_t leader_addr(uint32_t local_addr) {     // same offset in the shared memory of cluster rank 0
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local_addr));
@@ -160,7 +152,6 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     // arrives on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs have completed
@@ -361,7 +352,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
         if (rank == 0 && elect_one()) {
             constexpr uint32_t idesc_l1 = make_idesc(256, 64), idesc_128 = make_idesc(256, 128);
             mbar_wait(bar(BAR_W_FULL), 0);
-            mbar_wait_cluster(bar(BAR_WP_FULL), 0);
+            mbar_wait(bar(BAR_WP_FULL), 0);
             tc_fence_after();
             PROF_DECL;
             // Descriptors differ only in their 14-bit start-address field, so every MMA's pair is "base low word +
@@ -374,7 +365,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             auto issue_l3 = [&](int it, int cb, int hh) {   // layer 3 of pair-tile `it`: channel block cb, point half hh
                 const int q = it * 8 + cb * 2 + hh, b = q % kD3Bufs, buf = it & 1;   // A3_FULL of `it` was awaited by the caller
                 const uint32_t a3_lo = desc_lo(sbase + kSmA3 + buf * 32768 + hh * 8192, 16), d3 = tmem + kColD3 + b * 128;
-                PROF_WAIT(1, mbar_wait_cluster(bar(BAR_D3_EMPTY + b), ((q / kD3Bufs) & 1) ^ 1));
+                PROF_WAIT(1, mbar_wait(bar(BAR_D3_EMPTY + b), ((q / kD3Bufs) & 1) ^ 1));
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -387,11 +378,11 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             };
             for (int i = 0; i <= total; ++i) {
                 // H2 of pair-tile i-1 is ready in both CTAs and D2 (which D1 aliases) has been drained by both epilogues 2
-                if (i >= 1) PROF_WAIT(0, mbar_wait_cluster(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1));
+                if (i >= 1) PROF_WAIT(0, mbar_wait(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1));
                 if (i < total) {
                     const int s = i % kStages;
                     PROF_WAIT(3, mbar_wait(bar(BAR_X_FULL + s), (i / kStages) & 1));
-                    PROF_WAIT(3, mbar_wait_cluster(bar(BAR_XP_FULL + s), (i / kStages) & 1));
+                    PROF_WAIT(3, mbar_wait(bar(BAR_XP_FULL + s), (i / kStages) & 1));
                     tc_fence_after();
                     const uint32_t xa = sbase + kSmX + s * 2048;
                     tc_mma(tmem + kColD1, desc_at(desc_lo(xa, (sbase + kSmZero) - xa), hi_x, 0), desc_at(w1_lo, hi_x, 0), idesc_l1, 0);
@@ -401,7 +392,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 if (i >= 1) { issue_l3(i - 1, 0, 0); issue_l3(i - 1, 0, 1); if (kL2After >= 2) { issue_l3(i - 1, 1, 0); issue_l3(i - 1, 1, 1); } }
                 if (i < total) {
                     const uint32_t a2_lo = desc_lo(sbase + kSmA3 + (i & 1) * 32768, 16);
-                    PROF_WAIT(2, mbar_wait_cluster(bar(BAR_A2_FULL), i & 1));
+                    PROF_WAIT(2, mbar_wait(bar(BAR_A2_FULL), i & 1));
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)

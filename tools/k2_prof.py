@@ -23,7 +23,7 @@ tiles = n / (n_cta // 2) * -(-N // 256)   # pair-tiles (256 points) per CTA
 rows = [("issuer total", 0), ("issuer wait a3_full (H2 ready)", 1), ("issuer wait d3_empty", 2), ("issuer wait a2_full (H1 ready)", 3),
         ("issuer wait x_full", 4), ("front total", 8), ("front wait a3_empty", 9), ("front wait d1_full", 10),
         ("front wait d2_full", 11), ("maxpool total", 16), ("maxpool wait d3_full", 17), ("maxpool tmem load + wait::ld", 18),
-        ("maxpool fence + named barrier", 19), ("maxpool arrive d3_empty", 20)]
+        ("maxpool arrive d3_empty", 20)]
 print(f"n={n} N={N} tiles per CTA {tiles:.0f}")
 for nm, i in rows:
     col = p[:, i]
