@@ -211,6 +211,9 @@ def main():
     ap.add_argument("--k", type=int, default=8)
     ap.add_argument("--cpu-sample", type=int, default=1000, help="hypotheses in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inconst-th", type=float, default=100.0,
+                    help="free-space pre-filter threshold in percent (reference: 100 = off for LM-O, 10 for YCB-V, "
+                         "online_learning.py:174,184); the headline keeps it off so that every hypothesis is scored")
     args = ap.parse_args()
     quiet_stdout()
 
@@ -235,7 +238,7 @@ def main():
     intr, n_obj, per_gpu, n_pts, desc = WORKLOADS[args.workload]
     sc = make_workload(args.workload, world)
     w = [weights.seeded_folded(0), weights.seeded_folded(1)]
-    fs = scoring.FrameScorer(w, device=local, precision=args.precision, inconst_ratio_th=100.0, k=args.k)
+    fs = scoring.FrameScorer(w, device=local, precision=args.precision, inconst_ratio_th=args.inconst_th, k=args.k)
     weight_of = (lambda o: o % 2)          # two scorers keyed on object parity, online_learning.py:461-463
     total_hyp = sum(len(ob["pose_hypos"]) for ob in sc["objects"])
     local_hyp = sum(scoring.shard_range(len(ob["pose_hypos"]), rank, world)[1]
@@ -370,7 +373,8 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "hypotheses_per_step": total_hyp, "objects": n_obj,
-                   "points_per_object": n_pts, "topk": args.k, "inconst_ratio_th": 100.0,
+                   "points_per_object": n_pts, "topk": args.k, "inconst_ratio_th": args.inconst_th,
+                   "hypotheses_passing_prefilter": int(fs.last_scored) if args.inconst_th < 100 else total_hyp,
                    "parallelism": f"hypothesis-sharded x{world}, one all-gather of top-k" if world > 1 else "single GPU",
                    "l2": "feature chunks of 32768 hypotheses x 1000 pts (>= 0.5 GB) exceed the 126 MB L2; no flush needed",
                    "weights": "seeded random (no checkpoint is published)"},

@@ -109,6 +109,7 @@ class FrameScorer:
         self._scores = None
         self._resident = None
         self._segments = None
+        self.last_scored = 0          # hypotheses that passed the pre-filter in the last run_resident() on this rank
         self.forced_rank_world = None
         self.stage_events = None     # set to [] to record (stage, units, start_event, end_event) per launch group
 
@@ -194,6 +195,7 @@ class FrameScorer:
         for o in order:
             offs[o] = total
             total += n_keeps[o]
+        self.last_scored = total
         if self._pooled is None or self._pooled.shape[0] < total:
             self._pooled = torch.empty((max(total, 1), 1024), dtype=torch.float32, device=ctx.device)
             self._scores = torch.empty((max(total, 1),), dtype=torch.float32, device=ctx.device)
