@@ -36,7 +36,10 @@ WORKLOADS = {
     "c2": ("ycbv", 21, 10000, 1000, "YCB-V-shaped frame: 21 objects x 10,000 hypotheses x 1,000 pts"),
     "c3": ("lmo", 8, 50000, 1000, "LM-O-shaped frame: 8 objects x 50,000 hypotheses x 1,000 pts"),
     "c4": ("hd", 1, 200000, 4000, "bandwidth stress: 1280x720, 1 object x 200,000 hypotheses x 4,000 pts"),
+    # a step = the 32 frames scored between two finetune rounds (online_learning.py: finetune_interval); frames are C2-shaped
+    "c5": ("ycbv", 21, 10000, 1000, "online-learning stream: 32 frames x (21 objects x 10,000 hypotheses x 1,000 pts) per step"),
 }
+FRAMES_PER_STEP = {"c5": 32}
 MLP_MACS_PER_POINT = 8 * 64 + 64 * 128 + 128 * 1024
 HEAD_MACS = 1024 * 512 + 512 * 256 + 256
 
@@ -261,6 +264,9 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    n_frames = FRAMES_PER_STEP.get(args.workload, 1)
+    total_hyp *= n_frames
+    local_hyp *= n_frames
     for _ in range(args.warmup):
         S, I = fs.run_resident()
     barrier()
@@ -269,7 +275,7 @@ def main():
     l0 = fs.ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(args.steps * n_frames):
         S, I = fs.run_resident()
     e1.record()
     barrier()
@@ -292,12 +298,13 @@ def main():
     fs.score_frames([frame] * 2, weight_of)                       # warm-up (also builds the pinned cloud copies)
     barrier()
     t0 = time.perf_counter()
-    results = fs.score_frames([frame] * args.steps, weight_of)    # per frame: H2D of frame, clouds, poses; D2H of top-k
+    results = fs.score_frames([frame] * (args.steps * n_frames), weight_of)   # per frame: H2D of frame, clouds, poses; D2H of top-k
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
     Sh, Ih = results[-1]
-    h2d = img_h.numel() + dep_h.numel() * 4 + sum(3 * ob["model_points"].numel() * 4 for ob in host_objs) + local_hyp * 64
-    d2h = int(Sh.size * 4 + Ih.size * 4)
+    h2d = n_frames * (img_h.numel() + dep_h.numel() * 4 + sum(3 * ob["model_points"].numel() * 4 for ob in host_objs)) \
+        + local_hyp * 64
+    d2h = int(Sh.size * 4 + Ih.size * 4) * n_frames
     if not (np.array_equal(Ih, I.cpu().numpy()) and np.array_equal(Sh, S.cpu().numpy())):
         raise SystemExit("end-to-end result differs from the device-resident result")
 
@@ -372,7 +379,7 @@ def main():
         "metric": "hypotheses_scored_per_sec", "value": value, "unit": "hypotheses/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "hypotheses_per_step": total_hyp, "objects": n_obj,
+        "config": {"workload": f"{args.workload}: {desc}", "hypotheses_per_step": total_hyp, "frames_per_step": n_frames, "objects": n_obj,
                    "points_per_object": n_pts, "topk": args.k, "inconst_ratio_th": args.inconst_th,
                    "hypotheses_passing_prefilter": int(fs.last_scored) if args.inconst_th < 100 else total_hyp,
                    "parallelism": f"hypothesis-sharded x{world}, one all-gather of top-k" if world > 1 else "single GPU",
