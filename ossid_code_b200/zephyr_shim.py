@@ -32,6 +32,55 @@ def _meta_f(meta):
     return {k: float(np.asarray(v)) for k, v in meta.items()}
 
 
+class UvOriginal:
+    """``uv_original`` as the reference consumes it, without moving it: the reference keeps the (n, N_pts, 2) pixel
+    indices of ALL hypotheses only to read ``to_np(uv_original)[pred_idx]`` for the winner
+    (python/ossid/scripts/online_learning.py:474-478).  This object stays on the device (int32); ``.detach()``,
+    ``.cpu()`` and ``.numpy()`` -- the chain ``to_np`` applies (python/ossid/utils/__init__.py:166-173) -- are no-ops,
+    indexing copies just the requested rows to the host as int64, and ``np.asarray(...)`` / ``.to(...)`` /
+    ``.tensor()`` materialise the whole array for callers that really want it."""
+
+    dtype = np.dtype(np.int64)
+
+    def __init__(self, dev_i32: torch.Tensor):
+        self._dev = dev_i32
+
+    shape = property(lambda self: tuple(self._dev.shape))
+    ndim = property(lambda self: self._dev.dim())
+    device = property(lambda self: self._dev.device)
+
+    def __len__(self):
+        return self._dev.shape[0]
+
+    def detach(self):
+        return self
+
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        return self
+
+    def tensor(self) -> torch.Tensor:
+        return self._dev.to(torch.int64)
+
+    def to(self, *args, **kwargs):
+        return self.tensor().to(*args, **kwargs)
+
+    def __getitem__(self, idx):
+        if torch.is_tensor(idx):
+            idx = idx.to(self._dev.device)
+        elif isinstance(idx, np.ndarray):
+            idx = torch.from_numpy(idx).to(self._dev.device)
+        elif isinstance(idx, np.generic):
+            idx = idx.item()
+        return self._dev[idx].to(torch.int64).cpu().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.tensor().cpu().numpy()
+        return a if dtype is None else a.astype(dtype)
+
+
 class ScoreDataset:
     """``ScoreDataset(datapoints, dataset_root, dataset_name, args, mode='test')`` -- featuriser only.
 
@@ -53,6 +102,7 @@ class ScoreDataset:
         self.feature_dtype = torch.float32 if prec == "fp32" else torch.bfloat16
         self.device = getattr(args, "zs_device", 0)
         self.return_masks = False
+        self.lazy_uv = bool(getattr(args, "zs_lazy_uv", True))     # False: uv_original is a torch.int64 CUDA tensor
         self.last_mask = self.last_keep = None
 
     def getPointNetData(self, data, return_uv_original=False):
@@ -80,7 +130,7 @@ class ScoreDataset:
             if pe is not None:
                 data["pp_err"] = pe[kc.to(pe.device)] if torch.is_tensor(pe) else np.asarray(pe)[kc.numpy()]
         if return_uv_original:
-            return feat, uv.to(torch.int64)
+            return feat, (UvOriginal(uv) if self.lazy_uv else uv.to(torch.int64))
         return feat
 
 

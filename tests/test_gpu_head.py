@@ -173,3 +173,27 @@ def test_many_model_instances_do_not_share_stale_weights(ctx):
         for m, ref in zip(models, refs):
             got = m({"point_x": x}).reshape(-1).cpu()
             assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-6
+
+
+def test_uv_original_proxy_behaves_like_the_array_the_reference_reads(ctx):
+    """to_np(uv_original)[pred_idx] (online_learning.py:474-478) through the lazy device-side proxy == the full array."""
+    from ossid_code_b200 import zephyr_shim
+
+    class Args:
+        inconst_ratio_th = 100
+    sc = syn.make_scene(17, "lmo", n_obj=1, n_pts=200, n_hypo=64)
+    ob = sc["objects"][0]
+    data = dict(img=sc["img"], depth=sc["depth"], cam_K=sc["cam_K"], model_points=ob["model_points"],
+                model_colors=ob["model_colors"], model_normals=ob["model_normals"], pose_hypos=ob["pose_hypos"].copy())
+    ds = zephyr_shim.ScoreDataset([], "", "lmo", Args(), mode="test")
+    model = zephyr_shim.PointNet2SSG(8, Args(), num_class=1).to(0).eval()
+    poses, scores, err, uv = glue.networkInference(model, ds, data)
+    full = np.asarray(glue.to_np(uv))
+    assert isinstance(uv, zephyr_shim.UvOriginal) and full.dtype == np.int64 and full.shape == (64, 200, 2) == uv.shape
+    i = int(np.argmax(scores))
+    assert np.array_equal(glue.to_np(uv)[i], full[i]) and np.array_equal(uv[np.int64(i)], full[i])
+    assert np.array_equal(uv[torch.tensor([3, 1])], full[[3, 1]]) and torch.equal(uv.to("cpu"), torch.from_numpy(full))
+    Args.zs_lazy_uv = False
+    ds2 = zephyr_shim.ScoreDataset([], "", "lmo", Args(), mode="test")
+    _, _, _, uv2 = glue.networkInference(model, ds2, data)
+    assert torch.is_tensor(uv2) and uv2.dtype == torch.int64 and np.array_equal(uv2.cpu().numpy(), full)
