@@ -34,7 +34,7 @@ WORKLOADS = {
     # name: (intrinsics, n_obj, hypotheses per object per GPU, points per object, description)
     "c1": ("lmo", 1, 1000, 1000, "synthetic 640x480, 1 object x 1,000 hypotheses x 1,000 pts"),
     "c2": ("ycbv", 21, 10000, 1000, "YCB-V-shaped frame: 21 objects x 10,000 hypotheses x 1,000 pts"),
-    "c3": ("lmo", 8, 50000, 1000, "LM-O-shaped frame: 8 objects x 50,000 hypotheses x 1,000 pts"),
+    "c3": ("lmo", 8, 50000, 1000, "LM-O-shaped frame: 8 objects x 50,000 hypotheses x 1,000 pts, all inside DTOID-style box crops"),
     "c4": ("hd", 1, 200000, 4000, "bandwidth stress: 1280x720, 1 object x 200,000 hypotheses x 4,000 pts"),
     # a step = the 32 frames scored between two finetune rounds (online_learning.py: finetune_interval); frames are C2-shaped
     "c5": ("ycbv", 21, 10000, 1000, "online-learning stream: 32 frames x (21 objects x 10,000 hypotheses x 1,000 pts) per step"),
@@ -53,7 +53,7 @@ def load_peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
-def make_workload(name, n_gpus, seed=1):
+def make_workload(name, n_gpus, seed=1, gpu=True):
     """Synthetic frame for `name`; hypotheses per object scale with the GPU count (weak scaling)."""
     from ossid_code_b200 import synthetic as syn
     intr, n_obj, per_gpu, n_pts, _ = WORKLOADS[name]
@@ -61,11 +61,37 @@ def make_workload(name, n_gpus, seed=1):
     reps = -(-per_gpu * n_gpus // min(per_gpu, 10000))
     rng = np.random.default_rng(seed + 99)
     for ob in sc["objects"]:
-        if reps > 1:   # more hypotheses of the same mixture, freshly drawn
+        if name == "c3":
+            ob["pose_hypos"] = crop_hypotheses(sc, ob, rng, per_gpu * n_gpus, gpu)
+        elif reps > 1:   # more hypotheses of the same mixture, freshly drawn
             extra = [syn.make_hypotheses(rng, ob["gt_pose"], min(per_gpu, 10000), sc["cam_K"], sc["H"], sc["W"])
                      for _ in range(reps - 1)]
             ob["pose_hypos"] = np.concatenate([ob["pose_hypos"], *extra])[: per_gpu * n_gpus]
     return sc
+
+
+def crop_hypotheses(sc, ob, rng, n, gpu=True):
+    """C3: every hypothesis lies inside the object's DTOID-style box crop (GT box grown by expandBox's 1.2,
+    python/ossid/utils/__init__.py:11-16): draw from the usual mixture and keep what passes the reference's
+    filterHypoByMask(th=0.5) (python/ossid/utils/zephyr_utils.py:49-71; here the fused zs_mask_count kernel).
+    Workload preparation, outside every timed region."""
+    from ossid_code_b200 import synthetic as syn, zephyr_utils as glue
+    x1, y1, x2, y2 = syn.gt_box(sc, ob, 1.2)
+    mask = np.zeros((sc["H"], sc["W"]), np.uint8)
+    mask[y1:y2, x1:x2] = 1
+    meta, kept, have = glue.K2meta(sc["cam_K"]), [], 0
+    while have < n:
+        cand = syn.make_hypotheses(rng, ob["gt_pose"], 20000, sc["cam_K"], sc["H"], sc["W"])
+        if gpu:
+            keep = glue.filterHypoByMask(ob["model_points"], meta, cand, mask, th=0.5, device=torch.cuda.current_device())
+        else:                                     # reference arm: the CPU restatement of the same filter
+            from oracle import zephyr_oracle as zo
+            keep = zo.mask_filter(zo.project_raw(cand, ob["model_points"], meta), torch.from_numpy(mask.astype(np.int64)),
+                                  len(ob["model_points"]), th=0.5).numpy()
+        cand = cand[np.asarray(keep)]
+        kept.append(cand)
+        have += len(cand)
+    return np.concatenate(kept)[:n]
 
 
 class ClockSampler:
@@ -164,7 +190,7 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     intr, n_obj, per_gpu, n_pts, desc = WORKLOADS[args.workload]
-    sc = make_workload(args.workload, 1)
+    sc = make_workload(args.workload, 1, gpu=False)
     n_s = min(args.cpu_sample, per_gpu)
     sample = cpu_sample(sc, n_s)
     cpu_reference_run(sample, max(args.warmup, 1) if args.warmup else 0)
