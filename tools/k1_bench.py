@@ -26,6 +26,16 @@ if os.environ.get("ZS_SORT", "1") == "1":
     ob = {k: (v[perm] if k.startswith("model_") else v) for k, v in ob.items()}
     print("model points in Morton order")
 ctx.set_object(0, ob["model_points"], ob["model_colors"], ob["model_normals"])
+if os.environ.get("ZS_CROP", "0") != "0":
+    # C3-style: every hypothesis inside the DTOID-style box crop
+    box = syn.gt_box(sc, ob, 1.2)
+    mask = np.zeros((sc["H"], sc["W"]), np.uint8); mask[box[1]:box[3], box[0]:box[2]] = 1
+    kept = []
+    while sum(len(k) for k in kept) < n_hyp:
+        c = syn.make_hypotheses(rng, ob["gt_pose"], 20000, sc["cam_K"], sc["H"], sc["W"])
+        kept.append(c[glue.filterHypoByMask(ob["model_points"], glue.K2meta(sc["cam_K"]), c, mask, th=0.5)])
+    P = np.concatenate(kept)[:n_hyp]
+    print(f"hypotheses inside box {box} ({box[2]-box[0]} x {box[3]-box[1]} px, {(box[2]-box[0])*(box[3]-box[1])*16/1024:.0f} KB)")
 p12 = poses_to_rt12(P, ctx.device)
 peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6536.4
