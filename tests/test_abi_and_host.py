@@ -148,3 +148,22 @@ def test_allgather_topk_two_ranks_gloo():
         exp = sorted(range(40), key=lambda j: (-float(scores[o, j]), j))[:4]
         assert res[0][2][o] == exp
     assert res[0][2][1][:2] == [5, 33]
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (CPU restatement, no GPU needed): exactly one JSON line on stdout with the keys the
+    driver reads; the GPU arm prints the same keys plus roofline / clocks / gpu_launches."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample", "16"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"].startswith("c2")
