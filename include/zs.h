@@ -119,6 +119,15 @@ ZS_API int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, i
 ZS_API int zs_filter(zs_ctx* ctx, const int32_t* viol, int n, int n_pts, float inconst_ratio_th,
               int32_t* keep_idx_out, int32_t* n_keep_out, void* stream);
 
+/* Device-side hypothesis count for the calls that follow (no host read-back of zs_filter's count, so a filtered frame
+ * stays asynchronous): while n_dev [dev] int32[1] is set, zs_features (n_keep) and zs_pool with bf16 features (n)
+ * treat their count argument as a CAPACITY and process entries [n_offset, n_offset + capacity) of a list that has
+ * *n_dev entries, i.e. min(capacity, max(0, *n_dev - n_offset)) hypotheses; rows beyond that are left untouched.
+ * zs_score and the fp32 zs_pool return ZS_ERR_UNSUPPORTED while it is set; zs_head and zs_topk_segments are
+ * unaffected (run zs_head over the capacity and pass the device count through the segment table).
+ * n_dev = NULL restores host counts. */
+ZS_API int zs_set_dynamic_count(zs_ctx* ctx, const int32_t* n_dev, int n_offset);
+
 /* Second half of getPointNetData: features for hypotheses keep_idx[0..n_keep) of `poses`
  * (keep_idx NULL = all of 0..n_keep).  feat_out [dev] [n_keep][n_pts][8] float32 or bf16;
  * uv_out [dev] int32 [n_keep][n_pts][2] (nullable); mask_out [dev] uint8 [n_keep][n_pts]

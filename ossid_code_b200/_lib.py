@@ -24,6 +24,7 @@ SIGNATURES = {
     "zs_set_frame": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _f, _f, _p]),
     "zs_set_frame_u8": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _f, _f, _i, _p]),
     "zs_set_object": (_i, [_p, _i, _p, _p, _p, _i, _p]),
+    "zs_set_dynamic_count": (_i, [_p, _p, _i]),
     "zs_set_weights": (_i, [_p, _i, _p, C.c_size_t, _p]),
     "zs_project_uv": (_i, [_p, _p, _i, _p, _i, _f, _f, _f, _f, _p, _p]),
     "zs_mask_count": (_i, [_p, _p, _i, _p, _i, _f, _f, _f, _f, _p, _i, _i, _p, _p]),

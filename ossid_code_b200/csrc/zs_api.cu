@@ -229,6 +229,14 @@ extern "C" int zs_set_object(zs_ctx* ctx, int slot, const float* pts, const floa
     return ZS_OK;
 }
 
+extern "C" int zs_set_dynamic_count(zs_ctx* ctx, const int32_t* n_dev, int n_offset) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (n_dev && n_offset < 0) return zs_fail(ctx, ZS_ERR_INVALID, "n_offset %d", n_offset);
+    ctx->dyn_n = n_dev;
+    ctx->dyn_off = n_dev ? n_offset : 0;
+    return ZS_OK;
+}
+
 extern "C" int zs_set_weights(zs_ctx* ctx, int slot, const float* blob, size_t n_floats, void* stream) {
     if (!ctx) return ZS_ERR_INVALID;
     if (slot < 0 || slot >= ZS_MAX_WEIGHT_SLOTS) return zs_fail(ctx, ZS_ERR_INVALID, "weight slot %d", slot);

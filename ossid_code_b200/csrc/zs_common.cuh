@@ -47,6 +47,8 @@ struct zs_ctx {
     void* ws = nullptr;              // scratch (pooled vectors and the head's hidden layers)
     size_t ws_bytes = 0;
     void* tc_state = nullptr;        // owned by zs_score_tc.cu (tensor maps etc.)
+    const int32_t* dyn_n = nullptr;  // zs_set_dynamic_count: device-side hypothesis count for zs_features / zs_pool
+    int dyn_off = 0;
 };
 
 // offsets (in floats) into the weight blob
@@ -85,6 +87,14 @@ int zs_f32_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);  // zs_score
             return zs_fail((ctx), ZS_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__,         \
                            cudaGetErrorString(e_));                                             \
     } while (0)
+
+// Effective hypothesis count of a launch whose count lives on the device (zs_set_dynamic_count): entries
+// [n_off, n_off + n_cap) of a list of *n_dev.
+__device__ __forceinline__ int zs_dyn_count(const int32_t* __restrict__ n_dev, int n_off, int n_cap) {
+    if (!n_dev) return n_cap;
+    const int m = __ldg(n_dev) - n_off;
+    return m < 0 ? 0 : (m < n_cap ? m : n_cap);
+}
 
 // ---------------------------------------------------------------------------------------
 // Exact arithmetic.  The oracle performs one IEEE fp32 operation per step in a fixed order;

@@ -91,7 +91,9 @@ template <bool kBf16, bool kSmem, bool kAux>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 zs_k_features(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
               const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out,
-              int32_t* __restrict__ uv_out, uint8_t* __restrict__ mask_out, int32_t* __restrict__ viol_out) {
+              int32_t* __restrict__ uv_out, uint8_t* __restrict__ mask_out, int32_t* __restrict__ viol_out,
+              const int32_t* __restrict__ n_dev, int n_off) {
+    n_keep = zs_dyn_count(n_dev, n_off, n_keep);
     extern __shared__ __align__(16) char smem[];
     float4 *sA, *sB;
     float* sV;
@@ -218,7 +220,9 @@ __device__ __forceinline__ void st_f32_row(float* p, float4 lo, float4 hi, bool 
 template <bool kBf16, bool kSmem>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
-                  const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out, int aligned32) {
+                  const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out, int aligned32,
+                  const int32_t* __restrict__ n_dev, int n_off) {
+    n_keep = zs_dyn_count(n_dev, n_off, n_keep);
     extern __shared__ __align__(16) char smem[];
     float4 *sA, *sB;
     float* sV;
@@ -513,13 +517,15 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
             rc = opt_in_smem(ctx, zs_k_features<BF, SM, true>, smem);                          \
             if (rc) return rc;                                                                          \
             zs_k_features<BF, SM, true><<<grid, threads, smem, st>>>(                         \
-                o, cam, frame, poses, keep_idx, n_keep, feat_out, uv_out, mask_out, viol_out);          \
+                o, cam, frame, poses, keep_idx, n_keep, feat_out, uv_out, mask_out, viol_out,           \
+                ctx->dyn_n, ctx->dyn_off);                                                              \
         } else {                                                                                        \
             rc = opt_in_smem(ctx, zs_k_features_hot<BF, SM>, smem);                            \
             if (rc) return rc;                                                                          \
             zs_k_features_hot<BF, SM><<<grid, threads, smem, st>>>(o, cam, frame, poses,      \
                                                                   keep_idx, n_keep, feat_out,          \
-                                                                  (((uintptr_t)feat_out & 31) == 0));  \
+                                                                  (((uintptr_t)feat_out & 31) == 0),   \
+                                                                  ctx->dyn_n, ctx->dyn_off);           \
         }                                                                                               \
     } while (0)
     if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_FEAT(true, true); else ZS_LAUNCH_FEAT(true, false); }

@@ -228,6 +228,7 @@ static int head_impl(zs_ctx* ctx, int slot, const float* pooled, int n, float* s
 static int pool_impl(zs_ctx* ctx, int slot, const void* feat, int feat_dtype, int m, int n_pts, float* pooled, cudaStream_t st) {
     const zs_weights& w = ctx->w[slot];
     if (feat_dtype == ZS_F32) {
+        if (ctx->dyn_n) return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "device-side counts (zs_set_dynamic_count) need bf16 features");
         const size_t smem = (size_t)(8 + 64 + 128) * kRows * sizeof(float) + 1024 * sizeof(float);
         ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_mlp_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         f32_weights fw{w.f32t + kOffW1t, w.f32 + ZS_OFF_B1, w.f32t + kOffW2t, w.f32 + ZS_OFF_B2,
@@ -288,6 +289,7 @@ extern "C" int zs_score(zs_ctx* ctx, int weight_slot, const void* feat, int feat
     if (rc) return rc;
     if (precision != feat_dtype)
         return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "precision %d needs matching feature dtype (got %d)", precision, feat_dtype);
+    if (ctx->dyn_n) return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "device-side counts: use zs_pool + zs_head");
     if (n == 0) return ZS_OK;
     if (!scores_out) return zs_fail(ctx, ZS_ERR_INVALID, "scores_out");
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -259,7 +259,8 @@ __device__ __forceinline__ void max32(const uint32_t (&v)[32], float (&m)[4]) {
 __global__ void __launch_bounds__(kThreadsTc, 1)
 zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t* __restrict__ wimg,
             const float* __restrict__ wf32, float* __restrict__ pooled, float* __restrict__ dbg_h1,
-            float* __restrict__ dbg_h2) {
+            float* __restrict__ dbg_h2, const int32_t* __restrict__ n_dev, int n_off) {
+    n = zs_dyn_count(n_dev, n_off, n);          // zs_set_dynamic_count: the count may live on the device
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
@@ -580,7 +581,7 @@ static int launch_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, in
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ZS_CUDA(ctx, cudaLaunchKernelEx(&cfg, zs_k_mlp_tc, feat, n, n_pts, reinterpret_cast<const uint8_t*>(w.bf16),
-                                    (const float*)w.f32, pooled, dbg_h1, dbg_h2));
+                                    (const float*)w.f32, pooled, dbg_h1, dbg_h2, ctx->dyn_n, ctx->dyn_off));
     ZS_LAUNCHED(ctx);
     return ZS_OK;
 }

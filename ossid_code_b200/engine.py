@@ -171,6 +171,20 @@ class ZsContext:
                                     n_keep.data_ptr(), self._stream()), "zs_filter")
         return keep[: int(n_keep.item())]
 
+    def filter_async(self, viol, n_pts: int, th: float):
+        """As ``filter`` without the read-back: (keep indices, full length; kept count as a device int32[1] tensor)."""
+        n = viol.shape[0]
+        keep = torch.empty((max(n, 1),), dtype=torch.int32, device=self.device)
+        n_keep = torch.empty((1,), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.zs_filter(self.h, viol.data_ptr(), n, n_pts, float(th), keep.data_ptr(),
+                                    n_keep.data_ptr(), self._stream()), "zs_filter")
+        return keep, n_keep
+
+    def dynamic_count(self, n_dev: Optional[torch.Tensor], offset: int = 0):
+        """``zs_set_dynamic_count``: while set, ``features`` / ``pool`` (bf16) take their count from the device."""
+        self._ck(self.lib.zs_set_dynamic_count(self.h, n_dev.data_ptr() if n_dev is not None else None, int(offset)),
+                 "zs_set_dynamic_count")
+
     def features(self, slot: int, poses12, keep_idx: Optional[torch.Tensor] = None, n_keep: Optional[int] = None,
                  dtype=torch.float32, want_uv: bool = False, want_mask: bool = False, want_viol: bool = False,
                  out: Optional[torch.Tensor] = None):

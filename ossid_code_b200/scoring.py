@@ -109,9 +109,15 @@ class FrameScorer:
         self._scores = None
         self._resident = None
         self._segments = None
-        self.last_scored = 0          # hypotheses that passed the pre-filter in the last run_resident() on this rank
+        self._scored = (0, [], 0)     # see last_scored
         self.forced_rank_world = None
         self.stage_events = None     # set to [] to record (stage, units, start_event, end_event) per launch group
+
+    @property
+    def last_scored(self) -> int:
+        """Hypotheses that passed the pre-filter in the last run_resident() on this rank (reads device counts back)."""
+        total, devs, cap = self._scored
+        return total - cap + (int(torch.cat(devs).sum().item()) if devs else 0)
 
     def _mark(self, stage, units, prev=None):
         """Stage timing hook: closes the previous stage's CUDA-event pair and opens the next one."""
@@ -181,27 +187,35 @@ class FrameScorer:
         ctx, k = self.ctx, self.k
         res = self._resident
         tensor_cores = self.dtype == torch.bfloat16
-        # 1. free-space pre-filter per object (reads back one count per object when enabled)
-        keeps, n_keeps = [], []
+        # 1. free-space pre-filter per object.  Tensor-core path: the kept count stays on the device (the feature and
+        #    MLP kernels read it, zs_set_dynamic_count) and buffers are laid out by capacity, so a filtered frame is as
+        #    asynchronous as an unfiltered one.  fp32 parity path: reads back one count per object.
+        keeps, n_keeps, n_devs = [], [], []
         for r in res:
-            keep = None
-            if self.th < 100 and r["poses12"].shape[0] > 0:
-                keep = ctx.filter(ctx.violations(r["slot"], r["poses12"]), ctx.obj_npts[r["slot"]], self.th)
+            keep, n_dev, M = None, None, r["poses12"].shape[0]
+            if self.th < 100 and M > 0:
+                viol = ctx.violations(r["slot"], r["poses12"])
+                if tensor_cores:
+                    keep, n_dev = ctx.filter_async(viol, ctx.obj_npts[r["slot"]], self.th)
+                else:
+                    keep = ctx.filter(viol, ctx.obj_npts[r["slot"]], self.th)
             keeps.append(keep)
-            n_keeps.append(r["poses12"].shape[0] if keep is None else keep.shape[0])
+            n_devs.append(n_dev)
+            n_keeps.append(M if (keep is None or n_dev is not None) else keep.shape[0])     # capacity when the count is on the device
         # 2. objects laid out by weight slot so that the head runs once per scorer over a contiguous range
         order = sorted(range(len(res)), key=lambda o: res[o]["wslot"])
         offs, total = {}, 0
         for o in order:
             offs[o] = total
             total += n_keeps[o]
-        self.last_scored = total
+        self._scored = (total, [d for d in n_devs if d is not None],
+                        sum(n for n, d in zip(n_keeps, n_devs) if d is not None))
         if self._pooled is None or self._pooled.shape[0] < total:
-            self._pooled = torch.empty((max(total, 1), 1024), dtype=torch.float32, device=ctx.device)
-            self._scores = torch.empty((max(total, 1),), dtype=torch.float32, device=ctx.device)
+            self._pooled = torch.zeros((max(total, 1), 1024), dtype=torch.float32, device=ctx.device)
+            self._scores = torch.zeros((max(total, 1),), dtype=torch.float32, device=ctx.device)
         # 3. features -> shared MLP + max-pool, chunked so that the feature buffer stays bounded
         for o in order:
-            r, keep, n_keep = res[o], keeps[o], n_keeps[o]
+            r, keep, n_keep, n_dev = res[o], keeps[o], n_keeps[o], n_devs[o]
             poses12, N = r["poses12"], ctx.obj_npts[r["slot"]]
             for s in range(0, n_keep, self.chunk):
                 e = min(s + self.chunk, n_keep)
@@ -210,6 +224,8 @@ class FrameScorer:
                     self._feat = torch.empty((max(need, min(self.chunk, n_keep) * N * 8),), dtype=self.dtype,
                                              device=ctx.device)
                 feat = self._feat[:need].view(e - s, N, 8)
+                if n_dev is not None:
+                    ctx.dynamic_count(n_dev, s)
                 t = self._mark("features", (e - s) * N)
                 if keep is None:
                     ctx.features(r["slot"], poses12[s:e], n_keep=e - s, out=feat)
@@ -218,6 +234,8 @@ class FrameScorer:
                 t = self._mark("pool", (e - s) * N, t)
                 ctx.pool(r["wslot"], feat, out=self._pooled[offs[o] + s: offs[o] + e])
                 self._mark(None, 0, t)
+                if n_dev is not None:
+                    ctx.dynamic_count(None)
         # 4. head, one pass per scorer
         for ws in sorted({res[o]["wslot"] for o in order}):
             members = [o for o in order if res[o]["wslot"] == ws]
@@ -228,13 +246,23 @@ class FrameScorer:
                 ctx.head(ws, self._pooled[lo:hi], tensor_cores, out=self._scores[lo:hi])
                 self._mark(None, 0, t)
         # 5. per-object top-k in one launch (one CTA per object); indices mapped back to global hypothesis indices
-        #    inside the kernel.  The segment table only depends on the uploaded frame, so it is built once per upload
-        #    when no pre-filter is active (kept counts are then known on the host without a read-back).
+        #    inside the kernel.  Without a pre-filter the segment table only depends on the uploaded frame and is built
+        #    once per upload; with device-side counts it is assembled on the device (no read-back).
         if all(kp is None for kp in keeps):
             if self._segments is None:
                 self._segments = torch.tensor([[offs[o], n_keeps[o], r["lo"], 0] for o, r in enumerate(res)],
                                               dtype=torch.int32).pin_memory().to(ctx.device, non_blocking=True)
             S, I = ctx.topk_segments(self._scores, self._segments, k)
+        elif all(d is not None or n_keeps[o] == 0 for o, d in enumerate(n_devs)):
+            seg = torch.tensor([[offs[o], 0, r["lo"], 0] for o, r in enumerate(res)], dtype=torch.int32).pin_memory() \
+                .to(ctx.device, non_blocking=True)
+            zero = torch.zeros((1,), dtype=torch.int32, device=ctx.device)
+            seg[:, 1] = torch.cat([d if d is not None else zero for d in n_devs])
+            index_map = torch.zeros((max(total, 1),), dtype=torch.int32, device=ctx.device)
+            for o, d in enumerate(n_devs):
+                if d is not None:
+                    index_map[offs[o]: offs[o] + n_keeps[o]] = keeps[o][: n_keeps[o]]
+            S, I = ctx.topk_segments(self._scores, seg, k, index_map=index_map)
         else:
             top_s, top_i = [], []
             for o, r in enumerate(res):

@@ -197,3 +197,25 @@ def test_uv_original_proxy_behaves_like_the_array_the_reference_reads(ctx):
     ds2 = zephyr_shim.ScoreDataset([], "", "lmo", Args(), mode="test")
     _, _, _, uv2 = glue.networkInference(model, ds2, data)
     assert torch.is_tensor(uv2) and uv2.dtype == torch.int64 and np.array_equal(uv2.cpu().numpy(), full)
+
+
+def test_filtered_frame_with_device_side_counts_equals_the_synchronous_sequence(ctx):
+    """Pre-filter on (YCB-V setting, online_learning.py:184), tensor-core path: FrameScorer keeps the kept counts on the
+    device (zs_set_dynamic_count); the result must equal filter -> read count -> features -> pool -> head -> top-k run
+    call by call, bit for bit, including an object whose hypotheses are all rejected but one (never-empty rule)."""
+    sc = syn.make_scene(37, "lmo", n_obj=3, n_pts=300, n_hypo=700)
+    far = np.tile(np.eye(4), (50, 1, 1)); far[:, 2, 3] = 0.05                  # object 2: everything violates free space
+    sc["objects"][2]["pose_hypos"] = far
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    fs = scoring.FrameScorer(ws, device=0, precision="bf16", inconst_ratio_th=10.0, k=6, chunk=256)
+    S, I = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=lambda o: o % 2)
+    scored = fs.last_scored
+    n_kept = 0
+    for o, r in enumerate(fs._resident):
+        keep = ctx.filter(ctx.violations(r["slot"], r["poses12"]), ctx.obj_npts[r["slot"]], 10.0)
+        n_kept += keep.shape[0]
+        feat, _, _, _ = ctx.features(r["slot"], r["poses12"], keep_idx=keep, dtype=torch.bfloat16)
+        scores = ctx.head(r["wslot"], ctx.pool(r["wslot"], feat), tensor_cores=True)
+        es, ei = ctx.topk(scores, 6, r["lo"], index_map=keep)
+        assert np.array_equal(S[o], es.cpu().numpy()) and np.array_equal(I[o], ei.cpu().numpy()), (o, S[o], es, I[o], ei)
+    assert scored == n_kept and 0 < n_kept < 1450
