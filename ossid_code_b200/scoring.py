@@ -316,8 +316,9 @@ class FrameScorer:
         ``frames``: dicts with ``img`` (uint8), ``depth``, ``cam_K``, ``objects``.  Uploads, kernels and the
         read-back of each frame's top-k are all asynchronous; the host only blocks when ``depth`` frames are in
         flight, so the copies of frame f+1 overlap the kernels of frame f.  Returns a list of
-        ``(scores (n_obj,k), indices (n_obj,k))`` numpy pairs, one per frame.  With the free-space pre-filter
-        enabled (inconst_ratio_th < 100) each frame still synchronises once per object to read the kept count.
+        ``(scores (n_obj,k), indices (n_obj,k))`` numpy pairs, one per frame.  The free-space pre-filter
+        (inconst_ratio_th < 100) keeps its counts on the device on the tensor-core path; only the fp32 parity path
+        synchronises once per object to read the kept count.
         """
         stream = torch.cuda.current_stream(self.ctx.device)
         inflight, out = [], []
