@@ -36,6 +36,15 @@ if os.environ.get("ZS_CROP", "0") != "0":
         kept.append(c[glue.filterHypoByMask(ob["model_points"], glue.K2meta(sc["cam_K"]), c, mask, th=0.5)])
     P = np.concatenate(kept)[:n_hyp]
     print(f"hypotheses inside box {box} ({box[2]-box[0]} x {box[3]-box[1]} px, {(box[2]-box[0])*(box[3]-box[1])*16/1024:.0f} KB)")
+if os.environ.get("ZS_SORT_HYP", "0") == "1":
+    # hypotheses ordered by the image tile their translation projects to (what co-resident warps then share in L1)
+    K = sc["cam_K"]
+    t = P[:, :3, 3]
+    z = np.where(np.abs(t[:, 2]) > 1e-6, t[:, 2], 1e-6)
+    u = np.clip(t[:, 0] / z * K[0, 0] + K[0, 2], 0, sc["W"] - 1).astype(np.int64) // 32
+    v = np.clip(t[:, 1] / z * K[1, 1] + K[1, 2], 0, sc["H"] - 1).astype(np.int64) // 32
+    P = P[np.argsort(v * 64 + u, kind="stable")]
+    print("hypotheses sorted by projected 32x32 image tile")
 p12 = poses_to_rt12(P, ctx.device)
 peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6536.4
