@@ -397,7 +397,7 @@ def main():
             for key, stage in (("roofline", "zs_pool"), ("roofline_features", "zs_features")):
                 if key in roof and stage in tr:
                     roof[key]["traffic"] = tr[stage]["dram_read_bytes"] + tr[stage]["dram_write_bytes"]
-                    roof[key]["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, bytes per launch of 10,000 hypotheses)"
+                    roof[key]["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, bytes of the first captured launch: 10,000 hypotheses for the feature kernel, a 32,768-hypothesis chunk for the MLP kernel)"
     for key, per_unit in (("roofline", None), ("roofline_features", 48 + n_pts * 8 * fbytes)):
         if key in roof and per_unit:
             roof[key]["algorithmic_bytes_per_launch"] = per_unit * stages["features"]["units"] / n_pts / stages["features"]["calls"]

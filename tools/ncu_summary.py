@@ -65,7 +65,8 @@ os.makedirs(out_dir, exist_ok=True)
 open(os.path.join(out_dir, f"{tag}_ncu_summary.txt"), "w").write("\n".join(lines) + "\n")
 shutil.copy(launches, os.path.join(out_dir, f"{tag}_launches_c2.csv"))
 tj = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch, from one `ncu --set full --clock-control none` capture of "
-                  f"`{cmd}` (C2, bf16; every launch = 10,000 hypotheses x 1,000 points).  See {tag}_ncu_summary.txt.  Writes that "
+                  f"`{cmd}` (C2, bf16; the captured feature launch = 10,000 hypotheses x 1,000 points of one object, the captured MLP "
+                  f"launch = one 32,768-hypothesis chunk of a scorer's objects).  See {tag}_ncu_summary.txt.  Writes that "
                   "are still dirty in the 126 MB L2 when the kernel ends are not counted by these counters, hence traffic < "
                   "algorithmic bytes for the write-heavy feature kernel.",
       "workload": "c2", "precision": "bf16"}
