@@ -66,20 +66,54 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k: int):
     return s2[..., :k].contiguous(), i2[..., :k].contiguous()
 
 
-def allgather_topk(s: torch.Tensor, i: torch.Tensor, k: int, group=None):
-    """(n_obj,k) local candidates on each rank -> merged (n_obj,k), same on every rank."""
+def allgather_topk(s: torch.Tensor, i: torch.Tensor, k: int, group=None, ctx: Optional[ZsContext] = None):
+    """(n_obj,k) local candidates on each rank -> merged (n_obj,k), same on every rank.
+
+    One all-gather of (score bits, index) records, then the merge.  With a ``ctx`` (CUDA tensors) the merge is one
+    launch of the segmented top-k kernel over the (n_obj, world*k) candidates: they are laid out rank-major, every
+    rank's list is already ordered by (score desc, index asc) and ranks own ascending index ranges, so "position
+    ascending" is "global index ascending" among equal scores - the same rule as ``merge_topk``.
+    """
     import torch.distributed as dist
     world = dist.get_world_size(group)
     if world == 1:
         return merge_topk(s, i, k)
     # one record per candidate: score bits and index side by side (indices ship as int32, not as floats)
     rec = torch.stack([s.to(torch.float32).view(torch.int32), i.to(torch.int32)], dim=-1).contiguous()
-    parts = [torch.empty_like(rec) for _ in range(world)]
-    dist.all_gather(parts, rec, group=group)
-    out = torch.stack(parts)
-    gs = out[..., 0].view(torch.float32).permute(1, 0, 2).reshape(s.shape[0], -1)
-    gi = out[..., 1].permute(1, 0, 2).reshape(s.shape[0], -1)
-    return merge_topk(gs, gi.to(i.dtype), k)
+    if rec.is_cuda:
+        out = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
+        dist.all_gather_into_tensor(out, rec, group=group)
+    else:                                            # gloo (CPU tests) has no all_gather_into_tensor
+        parts = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(parts, rec, group=group)
+        out = torch.stack(parts)
+    cand = out.permute(1, 0, 2, 3).contiguous()                      # (n_obj, world, k, 2)
+    n_obj = s.shape[0]
+    gs = cand[..., 0].reshape(n_obj, world * k).view(torch.float32)
+    gi = cand[..., 1].reshape(n_obj, world * k)
+    return merge_gathered(gs, gi.to(i.dtype), k, ctx if s.is_cuda else None)
+
+
+def merge_gathered(gs: torch.Tensor, gi: torch.Tensor, k: int, ctx: Optional[ZsContext] = None):
+    """Merge rank-major candidate lists (n_obj, world*k) -> (n_obj,k): one segmented top-k launch (``ctx``) or the
+    torch reference ``merge_topk``; both order by (score desc, global index asc) with (-inf, -1) for empty slots."""
+    if ctx is None:
+        return merge_topk(gs, gi, k)
+    n_obj, width = gs.shape
+    gs = torch.where((gi < 0) | (gs != gs), torch.full_like(gs, float("-inf")), gs)       # empty slots and NaN never win
+    S, I = ctx.topk_segments(gs.reshape(-1).contiguous(), _merge_segments(n_obj, width, gs.device), k,
+                             index_map=gi.to(torch.int32).reshape(-1).contiguous())
+    return S, torch.where(S == float("-inf"), torch.full_like(I, -1), I).to(gi.dtype)
+
+
+_seg_cache = {}
+
+
+def _merge_segments(n_obj: int, width: int, device):
+    key = (n_obj, width, str(device))
+    if key not in _seg_cache:
+        _seg_cache[key] = torch.tensor([[o * width, width, 0, 0] for o in range(n_obj)], dtype=torch.int32, device=device)
+    return _seg_cache[key]
 
 
 class FrameScorer:
@@ -300,7 +334,7 @@ class FrameScorer:
             S, I = torch.stack(top_s), torch.stack(top_i)
         rank, world = self._rank_world()
         if world > 1 and self.forced_rank_world is None:
-            S, I = allgather_topk(S, I, k, self.group)
+            S, I = allgather_topk(S, I, k, self.group, ctx=ctx)
         return S, I
 
     # -- post-scoring refinement (online_learning.py:471-479) ----------------------------------

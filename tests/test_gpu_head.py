@@ -219,3 +219,27 @@ def test_filtered_frame_with_device_side_counts_equals_the_synchronous_sequence(
         es, ei = ctx.topk(scores, 6, r["lo"], index_map=keep)
         assert np.array_equal(S[o], es.cpu().numpy()) and np.array_equal(I[o], ei.cpu().numpy()), (o, S[o], es, I[o], ei)
     assert scored == n_kept and 0 < n_kept < 1450
+
+
+def test_kernel_merge_of_gathered_candidates_equals_torch_merge(ctx):
+    """The one-launch merge after the all-gather == merge_topk: ties across ranks, empty slots, a NaN, k > valid count."""
+    g = torch.Generator().manual_seed(11)
+    world, k, n_obj = 8, 6, 5
+    per = 1000
+    gs, gi = [], []
+    for r in range(world):                                   # every rank: k candidates ordered by (score desc, index asc)
+        s = torch.randn(n_obj, per, generator=g)
+        s[1, 7] = 5.0                                          # the same top score on every rank of object 1
+        if r == 3:
+            s[2, :] = float("nan")                             # a rank that only has NaNs for object 2
+        top = torch.stack([torch.tensor(sorted(range(per), key=lambda j: (-float(torch.nan_to_num(s[o, j], nan=-1e30)), j))[:k])
+                           for o in range(n_obj)])
+        gs.append(torch.gather(s, 1, top))
+        gi.append(top + r * per)
+    gs, gi = torch.stack(gs, 1).reshape(n_obj, world * k), torch.stack(gi, 1).reshape(n_obj, world * k).to(torch.int32)
+    gi[4, 3:] = -1                                             # object 4: only three real candidates in total
+    S0, I0 = scoring.merge_topk(gs.to(ctx.device), gi.to(ctx.device), k)
+    S1, I1 = scoring.merge_gathered(gs.to(ctx.device), gi.to(ctx.device), k, ctx)
+    assert torch.equal(I0, I1), (I0, I1)
+    assert torch.equal(S0, S1)
+    assert I1[1, :3].tolist() == [7, 1007, 2007] and I1[4, 3:].tolist() == [-1, -1, -1]
