@@ -26,7 +26,8 @@
 // epilogue (D3), warp 8 bulk-copy producer (weights once, then feature tiles, 3 stages), warp 9
 // TMEM allocator and -- in the leader CTA (rank 0) only -- the single elected MMA-issuing thread.  Completion
 // of MMAs reaches both CTAs through multicast tcgen05.commit; "operand ready" / "accumulator drained" travel
-// the other way as mbarrier arrivals on the leader's barriers (count 2: one local, one remote arrive).
+// the other way as per-warp mbarrier arrivals on the leader's barriers (count 8 = 4 epilogue warps x 2 CTAs).
+// There are no padding rows (see tile_row0), so the max-pool epilogue is a plain max over every accumulator column.
 // Front of pair-tile i+1 overlaps layer 3 of pair-tile i; D3 is triple-buffered in TMEM
 // (cols: D1 0-63 inside D2 0-127, D3 128-255 / 256-383 / 384-511).  H1 aliases the H2
 // buffer that the same tile's epilogue 2 overwrites afterwards, which is what makes two H2
