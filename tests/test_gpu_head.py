@@ -243,3 +243,35 @@ def test_kernel_merge_of_gathered_candidates_equals_torch_merge(ctx):
     assert torch.equal(I0, I1), (I0, I1)
     assert torch.equal(S0, S1)
     assert I1[1, :3].tolist() == [7, 1007, 2007] and I1[4, 3:].tolist() == [-1, -1, -1]
+
+
+@pytest.mark.parametrize("chunk", [96, 32768])
+def test_frame_scorer_paths_agree_batched_per_scorer_vs_per_object(ctx, chunk):
+    """No pre-filter: clouds of one size take the "one MLP launch per chunk of a scorer's objects" path, clouds of
+    different sizes the per-object path; both must equal scoring each object on its own (bit for bit), also when
+    chunk boundaries fall inside objects."""
+    sc = syn.make_scene(29, "lmo", n_obj=4, n_pts=256, n_hypo=150)
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    wof = lambda o: o % 2
+    fs = scoring.FrameScorer(ws, device=0, precision="bf16", inconst_ratio_th=100.0, k=5, chunk=chunk)
+
+    def alone(objects):
+        out = []
+        for o, ob in enumerate(objects):
+            one = scoring.FrameScorer(ws, device=0, precision="bf16", inconst_ratio_th=100.0, k=5)
+            S, I = one.score_frame(sc["img"], sc["depth"], sc["cam_K"], [dict(ob)], weight_of=lambda _: wof(o))
+            out.append((S[0], I[0]))
+        return out
+
+    S, I = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=wof)      # same sizes: batched
+    for o, (s1, i1) in enumerate(alone(sc["objects"])):
+        assert np.array_equal(S[o], s1) and np.array_equal(I[o], i1), o
+    mixed = [dict(ob) for ob in sc["objects"]]
+    for key in ("model_points", "model_colors", "model_normals"):
+        mixed[1][key] = mixed[1][key][:130].copy()                                                  # a smaller cloud
+    for ob in mixed:
+        ob.pop("_zs_host", None)
+    S2, I2 = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], mixed, weight_of=wof)              # per-object path
+    for o, (s1, i1) in enumerate(alone(mixed)):
+        assert np.array_equal(S2[o], s1) and np.array_equal(I2[o], i1), o
+    assert np.array_equal(S2[0], S[0]) and not np.array_equal(S2[1], S[1])
