@@ -181,9 +181,9 @@ class ZsContext:
         return keep, n_keep
 
     def dynamic_count(self, n_dev: Optional[torch.Tensor], offset: int = 0):
-        """``zs_set_dynamic_count``: while set, ``features`` / ``pool`` (bf16) take their count from the device."""
-        self._ck(self.lib.zs_set_dynamic_count(self.h, n_dev.data_ptr() if n_dev is not None else None, int(offset)),
-                 "zs_set_dynamic_count")
+        """``zs_set_dynamic_count``: while set, ``features`` / ``pool`` (bf16) take their count from the device.
+        Use as ``with ctx.dynamic_count(n_dev, offset): ...`` so that the host-count mode is always restored."""
+        return _DynamicCount(self, n_dev, offset)
 
     def features(self, slot: int, poses12, keep_idx: Optional[torch.Tensor] = None, n_keep: Optional[int] = None,
                  dtype=torch.float32, want_uv: bool = False, want_mask: bool = False, want_viol: bool = False,
@@ -312,6 +312,23 @@ class ZsContext:
                                            index_map.data_ptr() if index_map is not None and index_map.numel() else None,
                                            s.data_ptr(), i.data_ptr(), self._stream()), "zs_topk_segments")
         return s, i
+
+
+class _DynamicCount:
+    def __init__(self, ctx, n_dev, offset):
+        self.ctx, self.n_dev, self.offset = ctx, n_dev, int(offset)
+
+    def _set(self, t, off):
+        self.ctx._ck(self.ctx.lib.zs_set_dynamic_count(self.ctx.h, t.data_ptr() if t is not None else None, off),
+                     "zs_set_dynamic_count")
+
+    def __enter__(self):
+        self._set(self.n_dev, self.offset)
+        return self
+
+    def __exit__(self, *exc):
+        self._set(None, 0)
+        return False
 
 
 _contexts = {}

@@ -9,6 +9,7 @@ list, and the only data-path collective is one all-gather of k (score, index) re
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -286,18 +287,15 @@ class FrameScorer:
                     self._feat = torch.empty((max(need, min(self.chunk, n_keep) * N * 8),), dtype=self.dtype,
                                              device=ctx.device)
                 feat = self._feat[:need].view(e - s, N, 8)
-                if n_dev is not None:
-                    ctx.dynamic_count(n_dev, s)
-                t = self._mark("features", (e - s) * N)
-                if keep is None:
-                    ctx.features(r["slot"], poses12[s:e], n_keep=e - s, out=feat)
-                else:
-                    ctx.features(r["slot"], poses12, keep_idx=keep[s:e], out=feat)
-                t = self._mark("pool", (e - s) * N, t)
-                ctx.pool(r["wslot"], feat, out=self._pooled[offs[o] + s: offs[o] + e])
-                self._mark(None, 0, t)
-                if n_dev is not None:
-                    ctx.dynamic_count(None)
+                with (ctx.dynamic_count(n_dev, s) if n_dev is not None else contextlib.nullcontext()):
+                    t = self._mark("features", (e - s) * N)
+                    if keep is None:
+                        ctx.features(r["slot"], poses12[s:e], n_keep=e - s, out=feat)
+                    else:
+                        ctx.features(r["slot"], poses12, keep_idx=keep[s:e], out=feat)
+                    t = self._mark("pool", (e - s) * N, t)
+                    ctx.pool(r["wslot"], feat, out=self._pooled[offs[o] + s: offs[o] + e])
+                    self._mark(None, 0, t)
         # 4. head, one pass per scorer
         for ws in sorted({res[o]["wslot"] for o in order}):
             members = [o for o in order if res[o]["wslot"] == ws]
