@@ -58,6 +58,7 @@ class ZsContext:
         if rc != 0:
             raise _lib.ZsError(f"zs_create(device={self.index}) failed: {self.lib.zs_strerror(rc).decode()}")
         self.h = h
+        self.obj_token = {}
         self.frame_hw = None
         self.obj_npts = {}
 
@@ -113,7 +114,13 @@ class ZsContext:
                  "zs_set_frame_u8")
         self.frame_hw, self._keep = (H, W), (img, dep)
 
-    def set_object(self, slot: int, points, colors, normals):
+    def set_object(self, slot: int, points, colors, normals, token=None):
+        """Upload a model cloud into ``slot``.  ``token``: any object identifying the uploaded asset; a later call with
+        the same token (``is``) while the slot still holds it is skipped - clouds are static assets that the reference
+        loads once (online_learning.py:303-311)."""
+        if token is not None and self.obj_token.get(slot) is token:
+            return
+        self.obj_token[slot] = token
         p, c, n = (_dev_f32(t, self.device) for t in (points, colors, normals))
         if p.ndim != 2 or p.shape[1] != 3 or c.shape != p.shape or n.shape != p.shape:
             raise ValueError("model_points/colors/normals must all be (N,3)")

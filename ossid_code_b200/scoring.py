@@ -144,6 +144,7 @@ class FrameScorer:
         self._scores = None
         self._resident = None
         self._segments = None
+        self._copy_stream = None
         self._scored = (0, [], 0)     # see last_scored
         self.forced_rank_world = None
         self.stage_events = None     # set to [] to record (stage, units, start_event, end_event) per launch group
@@ -184,7 +185,26 @@ class FrameScorer:
         return 0, 1
 
     # -- upload (host -> HBM) ---------------------------------------------------------
-    def upload(self, img_u8, depth, cam_K, objects: List[dict], weight_of=lambda o: 0):
+    def prefetch_poses(self, objects: List[dict]):
+        """Start the host-to-device copy of this rank's pose slices on a side stream (the poses are >80 % of a frame's
+        upload bytes) so that it overlaps the kernels of the frame before; ``upload(..., prefetched=...)`` consumes it."""
+        ctx = self.ctx
+        rank, world = self._rank_world()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=ctx.device)
+        compute = torch.cuda.current_stream(ctx.device)
+        out = []
+        with torch.cuda.stream(self._copy_stream):
+            for ob in objects:
+                lo, hi = shard_range(len(ob["pose_hypos"]), rank, world)
+                p12 = poses_to_rt12(torch.as_tensor(ob["pose_hypos"])[lo:hi], ctx.device)
+                p12.record_stream(compute)              # allocated on the copy stream, read by kernels on the compute stream
+                out.append(p12)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return out, ev
+
+    def upload(self, img_u8, depth, cam_K, objects: List[dict], weight_of=lambda o: 0, prefetched=None):
         """Copy one frame's inputs to the device and keep them resident; this rank's pose slices only."""
         from .zephyr_utils import K2meta
         ctx = self.ctx
@@ -206,11 +226,14 @@ class FrameScorer:
                 host = tuple(t.contiguous().pin_memory() for t in (pts, cols, nrms))
                 ob["_zs_host"] = host
             pts, cols, nrms = host
-            ctx.set_object(slot, pts, cols, nrms)
+            ctx.set_object(slot, pts, cols, nrms, token=host)      # skipped when this slot already holds this cloud
             M = len(ob["pose_hypos"])
             lo, hi = shard_range(M, rank, world)
-            poses12 = poses_to_rt12(torch.as_tensor(ob["pose_hypos"])[lo:hi], ctx.device)
+            poses12 = prefetched[0][o] if prefetched is not None else \
+                poses_to_rt12(torch.as_tensor(ob["pose_hypos"])[lo:hi], ctx.device)
             res.append(dict(slot=slot, poses12=poses12, lo=lo, M=M, wslot=weight_of(o) % max(self.n_weights, 1)))
+        if prefetched is not None:
+            torch.cuda.current_stream(ctx.device).wait_event(prefetched[1])
         self._resident = res
         self._segments = None
         return res
@@ -375,7 +398,8 @@ class FrameScorer:
 
         ``frames``: dicts with ``img`` (uint8), ``depth``, ``cam_K``, ``objects``.  Uploads, kernels and the
         read-back of each frame's top-k are all asynchronous; the host only blocks when ``depth`` frames are in
-        flight, so the copies of frame f+1 overlap the kernels of frame f.  Returns a list of
+        flight, and the pose hypotheses of frame f+1 (most of a frame's bytes) travel on a side stream while the kernels
+        of frame f run.  Returns a list of
         ``(scores (n_obj,k), indices (n_obj,k))`` numpy pairs, one per frame.  The free-space pre-filter
         (inconst_ratio_th < 100) keeps its counts on the device on the tensor-core path; only the fp32 parity path
         synchronises once per object to read the kept count.
@@ -388,8 +412,10 @@ class FrameScorer:
             ev.synchronize()
             out.append((s_h.numpy().copy(), i_h.numpy().copy()))
 
-        for fr in frames:
-            self.upload(fr["img"], fr["depth"], fr["cam_K"], fr["objects"], weight_of)
+        nxt = self.prefetch_poses(frames[0]["objects"]) if frames else None
+        for f, fr in enumerate(frames):
+            self.upload(fr["img"], fr["depth"], fr["cam_K"], fr["objects"], weight_of, prefetched=nxt)
+            nxt = self.prefetch_poses(frames[f + 1]["objects"]) if f + 1 < len(frames) else None    # overlaps this frame's kernels
             S, I = self.run_resident()
             s_h = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
             i_h = torch.empty(I.shape, dtype=I.dtype, pin_memory=True)
