@@ -47,7 +47,10 @@ typedef enum {
     ZS_ERR_NOMEM = -5
 } zs_status;
 
-enum { ZS_F32 = 0, ZS_BF16 = 1 };
+/* element types: ZS_F32 / ZS_BF16 name feature and precision arguments; ZS_BF16_SPLIT features are two bf16 planes
+ * [2][n][n_pts][8] (hi = bf16(x), lo = bf16(x - hi)) feeding the 3-term fp32-accurate tensor-core scorer;
+ * ZS_F64 only names the source type of zs_pack_poses. */
+enum { ZS_F32 = 0, ZS_BF16 = 1, ZS_BF16_SPLIT = 2, ZS_F64 = 3 };
 
 #define ZS_DIM_POINT 8          /* channels of point_x: u_n v_n dH dS dV dD ncos 0 */
 #define ZS_MAX_OBJECTS 64
@@ -73,6 +76,16 @@ ZS_API void zs_destroy(zs_ctx* ctx);
 ZS_API const char* zs_last_error(const zs_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 ZS_API int64_t zs_launch_count(const zs_ctx* ctx);
+
+/* Sizes the context's scratch for scoring calls of up to max_hypotheses hypotheses, so that no later call allocates
+ * or frees device memory between the kernels of a frame (allocation synchronises the device).  Optional: without
+ * it the scratch grows on demand. */
+ZS_API int zs_reserve(zs_ctx* ctx, int max_hypotheses);
+
+/* Pose hand-over: transforms [dev] (n,4,4) row-major, dtype ZS_F32 or ZS_F64 (the reference hands float64 over,
+ * python/ossid/utils/zephyr_utils.py:16) -> poses_out [dev] float32 [n][12] rows of (R | t): the single IEEE
+ * round-to-nearest cast of `transforms[:, :3, :4]`. */
+ZS_API int zs_pack_poses(zs_ctx* ctx, const void* transforms, int dtype, int n, float* poses_out, void* stream);
 
 /* Frame upload.  Replaces the tensors built at python/ossid/utils/zephyr_utils.py:13-17.
  * zs_set_frame: rgb [dev] float32 H*W*3 in [0,1] (already blurred and divided by 255),
@@ -115,9 +128,11 @@ ZS_API int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, i
 /* Hypothesis pre-filter of getPointNetData (its effect is visible at zephyr_utils.py:39-43;
  * thresholds online_learning.py:174,184): keep h iff viol[h]*100/n_pts < th (th >= 100
  * keeps all); never empty (first minimum kept).  keep_idx_out [dev] int32 [n] ascending,
- * n_keep_out [dev] int32[1]. */
+ * n_keep_out [dev] int32[1].  info_out [dev] int32[2] (nullable) = {hypotheses that really passed the test (0 when
+ * the never-empty rule supplied the single kept one), violation count of that fallback}: what zs_merge_topk needs to
+ * apply the never-empty rule to the object's WHOLE list when the list is sharded over GPUs. */
 ZS_API int zs_filter(zs_ctx* ctx, const int32_t* viol, int n, int n_pts, float inconst_ratio_th,
-              int32_t* keep_idx_out, int32_t* n_keep_out, void* stream);
+              int32_t* keep_idx_out, int32_t* n_keep_out, int32_t* info_out, void* stream);
 
 /* Device-side hypothesis count for the calls that follow (no host read-back of zs_filter's count, so a filtered frame
  * stays asynchronous): while n_dev [dev] int32[1] is set, zs_features (n_keep) and zs_pool with bf16 features (n)
@@ -160,16 +175,39 @@ ZS_API int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat_bf16, in
 /* Per-object top-k, ordered by (score desc, index asc); k <= ZS_MAX_TOPK.  Generalises
  * `scores.argmax()` (online_learning.py:466-467; first maximum wins ties).
  * s_out [dev] float32 [k], i_out [dev] int32 [k] = index_map[i] + index_base (index_map [dev] int32 [n],
- * NULL = identity; pass zs_filter's keep_idx to get indices into the unfiltered hypothesis list);
- * entries beyond n are (-inf, -1). */
+ * NULL = identity; pass zs_filter's keep_idx to get indices into the unfiltered hypothesis list; an entry whose
+ * index_map value is negative is an empty slot and is skipped); a NaN score never beats a real one and is reported
+ * as -inf; output slots beyond the candidates are (-inf, -1). */
 ZS_API int zs_topk(zs_ctx* ctx, const float* scores, int n, int k, int index_base, const int32_t* index_map,
             float* s_out, int32_t* i_out, void* stream);
 
 /* The same for all objects of a frame in one launch (one CTA per object).  segments [dev] int32 [n_segments][4] =
- * {first score, count, index_base, 0}; scores [dev] and index_map [dev] (nullable) are indexed by first score + i.
+ * {first score, count, index_base, map_delta}; scores [dev] are indexed by first score + i, index_map [dev]
+ * (nullable) by first score + map_delta + i (map_delta = 0: the two arrays share one layout).
  * s_out [dev] float32 [n_segments][k], i_out [dev] int32 [n_segments][k]. */
 ZS_API int zs_topk_segments(zs_ctx* ctx, const float* scores, const int32_t* segments, int n_segments, int k,
                      const int32_t* index_map, float* s_out, int32_t* i_out, void* stream);
+
+/* Multi-GPU merge (the reduction the reference does with one argmax, online_learning.py:466-467, after the hypothesis
+ * list has been sharded): gathered [dev] int32 [world][rec_ints] = the all-gathered per-rank records, each
+ *   [0, n_obj*k) score bits | [n_obj*k, 2*n_obj*k) global hypothesis indices (-1 = empty) |
+ *   [2*n_obj*k, 2*n_obj*k + 2*n_obj) zs_filter's info_out per object ({1, 0} when no pre-filter ran) |
+ *   (only when poses_out != NULL; starts at the next multiple of 4 ints) n_obj*k*12 floats: the candidates'
+ *   poses (zs_gather_poses),
+ * rank r holding hypotheses of a lower index range than rank r+1.  Output per object: the k best of all ranks by
+ * (score desc, index asc), with the never-empty rule of zs_filter applied to the whole list (fallback candidates are
+ * dropped when any rank kept a hypothesis; otherwise only the first minimum-violation one survives).  Identical on
+ * every rank and identical to the unsharded result.  s_out [dev] float32 [n_obj][k], i_out [dev] int32 [n_obj][k],
+ * poses_out [dev] float32 [n_obj][k][12] (nullable): the winners' poses, for the fp32 re-rank. */
+ZS_API int zs_merge_topk(zs_ctx* ctx, const int32_t* gathered, int world, int rec_ints, int n_obj, int k,
+                  float* s_out, int32_t* i_out, float* poses_out, void* stream);
+
+/* Poses of the top-k candidates: out [dev] float32 [n_seg][k][12] = poses[segments[g].first_row + idx[g][j] -
+ * segments[g].index_base] for idx [dev] int32 [n_seg][k] >= 0 (zeros otherwise); segments [dev] int32 [n_seg][4] =
+ * {first pose row of the object, index_base, 0, 0}.  The k winners' poses travel with the all-gathered record so that
+ * any rank can re-score any candidate (the fp32-accurate re-rank that makes top-1 independent of the bf16 rounding). */
+ZS_API int zs_gather_poses(zs_ctx* ctx, const float* poses, const int32_t* idx, const int32_t* segments, int n_seg, int k,
+                    float* out, void* stream);
 
 /* Batched ADD / ADI pose error of every hypothesis against one ground-truth pose; replaces the Python loop
  * `[err_func(R, t, R_gt, t_gt, model_points) for mat in poses_all]` (online_learning.py:452, err_func = add | adi

@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ZS_LIB") or os.path.join(HERE, "libzs.so")   # ZS_LIB: A/B builds in tools/
 
-ZS_F32, ZS_BF16 = 0, 1
+ZS_F32, ZS_BF16, ZS_BF16_SPLIT, ZS_F64 = 0, 1, 2, 3
 ZS_MAX_TOPK = 64
 ZS_WEIGHT_FLOATS = 64 * 8 + 64 + 128 * 64 + 128 + 1024 * 128 + 1024 + 512 * 1024 + 512 + 256 * 512 + 256 + 256 + 1
 
@@ -29,7 +29,11 @@ SIGNATURES = {
     "zs_project_uv": (_i, [_p, _p, _i, _p, _i, _f, _f, _f, _f, _p, _p]),
     "zs_mask_count": (_i, [_p, _p, _i, _p, _i, _f, _f, _f, _f, _p, _i, _i, _p, _p]),
     "zs_violations": (_i, [_p, _i, _p, _i, _p, _p]),
-    "zs_filter": (_i, [_p, _p, _i, _i, _f, _p, _p, _p]),
+    "zs_filter": (_i, [_p, _p, _i, _i, _f, _p, _p, _p, _p]),
+    "zs_reserve": (_i, [_p, _i]),
+    "zs_pack_poses": (_i, [_p, _p, _i, _i, _p, _p]),
+    "zs_merge_topk": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "zs_gather_poses": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "zs_features": (_i, [_p, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
     "zs_score": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p]),
     "zs_pool": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),

@@ -16,7 +16,8 @@ int zs_fail(zs_ctx* ctx, int code, const char* fmt, ...) {
 
 int zs_reserve_ws(zs_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->ws_bytes) return ZS_OK;
-    // grow-only scratch; cudaFree synchronises the device, which orders it after pending users
+    // Grow-only scratch; cudaFree synchronises the device, which orders it after pending users.  Steady-state callers
+    // size it once up front with zs_reserve() so that no allocation happens between the kernels of a frame.
     if (ctx->ws) ZS_CUDA(ctx, cudaFree(ctx->ws));
     ctx->ws = nullptr;
     ctx->ws_bytes = 0;
@@ -29,7 +30,36 @@ int zs_reserve_ws(zs_ctx* ctx, size_t bytes) {
     return ZS_OK;
 }
 
-extern "C" int zs_version(void) { return 100; }
+extern "C" int zs_version(void) { return 200; }
+
+extern "C" int zs_reserve(zs_ctx* ctx, int max_hypotheses) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (max_hypotheses < 0) return zs_fail(ctx, ZS_ERR_INVALID, "max_hypotheses %d", max_hypotheses);
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t chunk = max_hypotheses < ZS_SCORE_CHUNK ? max_hypotheses : ZS_SCORE_CHUNK;
+    return zs_reserve_ws(ctx, chunk * (1024 + 512 + 256) * sizeof(float));
+}
+
+// transforms (n,4,4) float32 or float64, row-major -> poses [n][12] float32 rows of (R | t): the one cast of the
+// hand-over (python/ossid/utils/zephyr_utils.py:16, float64) to the kernels' float32, IEEE round-to-nearest.
+template <typename T>
+__global__ void zs_k_pack_poses(const T* __restrict__ src, int n, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * 12) dst[i] = (float)src[(size_t)(i / 12) * 16 + (i % 12)];     // the first 12 of 16 are rows 0-2
+}
+
+extern "C" int zs_pack_poses(zs_ctx* ctx, const void* transforms, int dtype, int n, float* poses_out, void* stream) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (n == 0) return ZS_OK;
+    if (n < 0 || n > (1 << 27) || !transforms || !poses_out || (dtype != ZS_F32 && dtype != ZS_F64))
+        return zs_fail(ctx, ZS_ERR_INVALID, "zs_pack_poses n %d dtype %d", n, dtype);
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int grid = (n * 12 + 255) / 256;
+    if (dtype == ZS_F32) zs_k_pack_poses<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)transforms, n, poses_out);
+    else zs_k_pack_poses<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)transforms, n, poses_out);
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
 
 extern "C" const char* zs_strerror(int status) {
     switch (status) {
@@ -144,6 +174,7 @@ static int zs_frame_common(zs_ctx* ctx, int H, int W, float fx, float fy, float 
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t n_px = (size_t)H * W;
     if (n_px > ctx->frame.cap_px) {
+        ctx->frame.set = false;             // stays unset if the regrow fails (zs_features then reports ZS_ERR_STATE)
         ZS_CUDA(ctx, cudaFree(ctx->frame.packed));
         ctx->frame.packed = nullptr;
         ctx->frame.cap_px = 0;

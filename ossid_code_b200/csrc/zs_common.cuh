@@ -10,6 +10,7 @@
 
 #include "../../include/zs.h"
 
+#define ZS_SCORE_CHUNK 32768    // hypotheses per scoring chunk (bounds the head's workspace)
 #define ZS_DEPTH_MARGIN 0.02f   // metres; reference: python/ossid/datasets/ycbv_sift_dataset.py:325
 
 struct zs_frame {

@@ -387,7 +387,7 @@ zs_k_project(const float* __restrict__ poses, int n, const float* __restrict__ p
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 zs_k_filter(const int32_t* __restrict__ viol, int n, float n_pts_f, float th, int32_t* __restrict__ keep_idx,
-            int32_t* __restrict__ n_keep_out) {
+            int32_t* __restrict__ n_keep_out, int32_t* __restrict__ info_out) {
     __shared__ int s_warp[32];
     __shared__ int s_total;
     __shared__ unsigned long long s_min;
@@ -430,6 +430,10 @@ zs_k_filter(const int32_t* __restrict__ viol, int n, float n_pts_f, float th, in
     __syncthreads();
     if (threadIdx.x == 0) {
         int nk = base_out;
+        if (info_out) {                // what a multi-GPU merge needs to apply the never-empty rule globally
+            info_out[0] = base_out;                                   // hypotheses that really passed the test
+            info_out[1] = n > 0 ? (int)(s_min >> 32) : 0;             // violation count of the fallback candidate
+        }
         if (nk == 0 && n > 0) {        // never empty
             keep_idx[0] = (int)(s_min & 0xffffffffull);
             nk = 1;
@@ -559,12 +563,13 @@ extern "C" int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int 
 }
 
 extern "C" int zs_filter(zs_ctx* ctx, const int32_t* viol, int n, int n_pts, float inconst_ratio_th,
-                         int32_t* keep_idx_out, int32_t* n_keep_out, void* stream) {
+                         int32_t* keep_idx_out, int32_t* n_keep_out, int32_t* info_out, void* stream) {
     if (!ctx) return ZS_ERR_INVALID;
     if (n < 0 || n_pts <= 0 || !n_keep_out || (n > 0 && (!viol || !keep_idx_out)))
         return zs_fail(ctx, ZS_ERR_INVALID, "zs_filter arguments");
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
-    zs_k_filter<<<1, 1024, 0, (cudaStream_t)stream>>>(viol, n, (float)n_pts, inconst_ratio_th, keep_idx_out, n_keep_out);
+    zs_k_filter<<<1, 1024, 0, (cudaStream_t)stream>>>(viol, n, (float)n_pts, inconst_ratio_th, keep_idx_out, n_keep_out,
+                                                      info_out);
     ZS_LAUNCHED(ctx);
     return ZS_OK;
 }

@@ -27,6 +27,8 @@ constexpr uint32_t kFcBar = kFcStages * kStageBytes;          // barriers after 
 constexpr uint32_t kFcTmemPtr = kFcBar + 128;
 constexpr uint32_t kFcSmAlloc = kFcTmemPtr + 16 + 1024;
 static_assert(kFcSmAlloc <= 232448, "exceeds 227 KB of shared memory per CTA");
+// fc2's fused fc3 epilogue writes out[row] = partial dot + c3 from ONE CTA per row tile: it needs grid.x = 256 / kBN = 1
+static_assert(kBN == 256, "the fused fc3 epilogue assumes one CTA covers all 256 channels of fc2");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -190,7 +190,7 @@ __global__ void zs_k_transpose(const float* __restrict__ W, float* __restrict__ 
 
 constexpr int kOffW1t = 0, kOffW2t = kOffW1t + 8 * 64, kOffW3t = kOffW2t + 64 * 128,
               kOffF1t = kOffW3t + 128 * 1024, kOffF2t = kOffF1t + 1024 * 512, kTransFloats = kOffF2t + 512 * 256;
-constexpr int kScoreChunk = 32768;   // hypotheses per scoring chunk (bounds the workspace)
+constexpr int kScoreChunk = ZS_SCORE_CHUNK;
 
 }  // namespace
 

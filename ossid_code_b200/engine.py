@@ -12,9 +12,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ZS_BF16, ZS_F32, check
+from ._lib import ZS_BF16, ZS_F32, ZS_F64, check
 
 FEAT_DTYPES = {torch.float32: ZS_F32, torch.bfloat16: ZS_BF16}
+POSE_DTYPES = {torch.float32: ZS_F32, torch.float64: ZS_F64}
 
 
 def _dev_f32(x, device) -> torch.Tensor:
@@ -30,7 +31,8 @@ def poses_to_rt12(transforms, device) -> torch.Tensor:
     """(M,4,4) any float dtype -> (M,12) float32 rows of (R|t) on ``device`` (include/zs.h).
 
     The whole (M,16) block is copied as is (asynchronously when the source is pinned) and sliced / cast
-    once to float32 on the device; IEEE round-to-nearest either side, so the values equal a host cast.
+    once to float32 by ``zs_pack_poses`` on the device; IEEE round-to-nearest either side, so the values equal a
+    host cast.
     """
     t = torch.as_tensor(transforms)
     if t.ndim != 3 or t.shape[1:] != (4, 4):
@@ -41,7 +43,7 @@ def poses_to_rt12(transforms, device) -> torch.Tensor:
     if dev.type == "cpu":
         return t[:, :3, :4].to(torch.float32).reshape(t.shape[0], 12).contiguous()
     t = t.contiguous().to(dev, non_blocking=True)
-    return t[:, :3, :4].to(torch.float32).reshape(t.shape[0], 12).contiguous()
+    return get_context(dev).pack_poses(t)
 
 
 class ZsContext:
@@ -61,6 +63,7 @@ class ZsContext:
         self.obj_token = {}
         self.frame_hw = None
         self.obj_npts = {}
+        self.weight_owner = {}        # slot -> token of whoever uploaded last (see set_weights)
 
     def close(self):
         if getattr(self, "h", None):
@@ -120,23 +123,43 @@ class ZsContext:
         loads once (online_learning.py:303-311)."""
         if token is not None and self.obj_token.get(slot) is token:
             return
-        self.obj_token[slot] = token
+        self.obj_token.pop(slot, None)          # the slot is only credited with the new cloud once the upload succeeded
         p, c, n = (_dev_f32(t, self.device) for t in (points, colors, normals))
         if p.ndim != 2 or p.shape[1] != 3 or c.shape != p.shape or n.shape != p.shape:
             raise ValueError("model_points/colors/normals must all be (N,3)")
         self._ck(self.lib.zs_set_object(self.h, slot, p.data_ptr(), c.data_ptr(), n.data_ptr(), p.shape[0],
                                         self._stream()), "zs_set_object")
         self.obj_npts[slot] = p.shape[0]
+        self.obj_token[slot] = token
         self._keep_obj = (p, c, n)
 
-    def set_weights(self, slot: int, folded: dict):
+    def set_weights(self, slot: int, folded: dict, owner=None):
+        """Upload folded weights into ``slot``.  ``owner``: token of the uploader; users that share a context check
+        ``weight_owner[slot] is their token`` before every launch and re-upload when someone else took the slot."""
         from .weights import FOLDED_KEYS
+        self.weight_owner.pop(slot, None)
         blob = torch.cat([folded[k].detach().to(torch.float32).reshape(-1).cpu() for k in FOLDED_KEYS])
         if blob.numel() != _lib.ZS_WEIGHT_FLOATS:
             raise ValueError(f"folded weights have {blob.numel()} values, expected {_lib.ZS_WEIGHT_FLOATS}")
         blob = blob.to(self.device)
         self._ck(self.lib.zs_set_weights(self.h, slot, blob.data_ptr(), blob.numel(), self._stream()), "zs_set_weights")
         torch.cuda.current_stream(self.device).synchronize()   # blob may be freed after return
+        self.weight_owner[slot] = owner
+
+    def reserve(self, max_hypotheses: int):
+        """Size the library's scratch once (no allocation between the kernels of later frames)."""
+        self._ck(self.lib.zs_reserve(self.h, int(max_hypotheses)), "zs_reserve")
+
+    def pack_poses(self, transforms: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Device (n,4,4) float32 / float64 -> (n,12) float32 rows of (R|t), one kernel."""
+        n = transforms.shape[0]
+        if not transforms.is_cuda or not transforms.is_contiguous() or transforms.dtype not in POSE_DTYPES:
+            raise ValueError("pack_poses needs a contiguous float32/float64 CUDA tensor (n,4,4)")
+        if out is None:
+            out = torch.empty((n, 12), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.zs_pack_poses(self.h, transforms.data_ptr() if n else None, POSE_DTYPES[transforms.dtype], n,
+                                        out.data_ptr() if n else None, self._stream()), "zs_pack_poses")
+        return out
 
     # -- kernels ----------------------------------------------------------------------
     def project_uv(self, poses12, points, meta) -> torch.Tensor:
@@ -162,29 +185,29 @@ class ZsContext:
                  "zs_mask_count")
         return cnt
 
-    def violations(self, slot: int, poses12) -> torch.Tensor:
+    def violations(self, slot: int, poses12, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         n = poses12.shape[0]
-        viol = torch.empty((n,), dtype=torch.int32, device=self.device)
+        viol = out if out is not None else torch.empty((n,), dtype=torch.int32, device=self.device)
         self._ck(self.lib.zs_violations(self.h, slot, poses12.data_ptr(), n, viol.data_ptr(), self._stream()),
                  "zs_violations")
         return viol
 
     def filter(self, viol, n_pts: int, th: float) -> torch.Tensor:
         """Kept hypothesis indices (ascending, int32).  Reads the count back: one 4-byte sync."""
-        n = viol.shape[0]
-        keep = torch.empty((max(n, 1),), dtype=torch.int32, device=self.device)
-        n_keep = torch.empty((1,), dtype=torch.int32, device=self.device)
-        self._ck(self.lib.zs_filter(self.h, viol.data_ptr(), n, n_pts, float(th), keep.data_ptr(),
-                                    n_keep.data_ptr(), self._stream()), "zs_filter")
+        keep, n_keep = self.filter_async(viol, n_pts, th)
         return keep[: int(n_keep.item())]
 
-    def filter_async(self, viol, n_pts: int, th: float):
-        """As ``filter`` without the read-back: (keep indices, full length; kept count as a device int32[1] tensor)."""
+    def filter_async(self, viol, n_pts: int, th: float, info: Optional[torch.Tensor] = None,
+                     keep_out: Optional[torch.Tensor] = None, n_keep_out: Optional[torch.Tensor] = None):
+        """As ``filter`` without the read-back: (keep indices, full length; kept count as a device int32[1] tensor).
+        ``info``: optional device int32[2] that receives {really kept, fallback violation count} (zs_merge_topk);
+        ``keep_out`` / ``n_keep_out``: caller-owned outputs (contiguous int32 views)."""
         n = viol.shape[0]
-        keep = torch.empty((max(n, 1),), dtype=torch.int32, device=self.device)
-        n_keep = torch.empty((1,), dtype=torch.int32, device=self.device)
+        keep = keep_out if keep_out is not None else torch.empty((max(n, 1),), dtype=torch.int32, device=self.device)
+        n_keep = n_keep_out if n_keep_out is not None else torch.empty((1,), dtype=torch.int32, device=self.device)
         self._ck(self.lib.zs_filter(self.h, viol.data_ptr(), n, n_pts, float(th), keep.data_ptr(),
-                                    n_keep.data_ptr(), self._stream()), "zs_filter")
+                                    n_keep.data_ptr(), info.data_ptr() if info is not None else None, self._stream()),
+                 "zs_filter")
         return keep, n_keep
 
     def dynamic_count(self, n_dev: Optional[torch.Tensor], offset: int = 0):
@@ -309,12 +332,46 @@ class ZsContext:
                                         out.data_ptr(), self._stream()), "zs_visib_mask")
         return out.to(torch.bool)
 
-    def topk_segments(self, scores: torch.Tensor, segments: torch.Tensor, k: int, index_map: Optional[torch.Tensor] = None):
+    def merge_topk(self, gathered: torch.Tensor, n_obj: int, k: int, out=None, poses_out: Optional[torch.Tensor] = None):
+        """``zs_merge_topk`` over all-gathered records (world, rec_ints) int32 -> (n_obj,k) scores, indices;
+        ``poses_out`` (n_obj,k,12) float32 also receives the winners' poses when the records carry them."""
+        world, rec_ints = gathered.shape
+        if out is not None:
+            s, i = out
+        else:
+            s = torch.empty((n_obj, k), dtype=torch.float32, device=self.device)
+            i = torch.empty((n_obj, k), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.zs_merge_topk(self.h, gathered.data_ptr(), world, rec_ints, n_obj, k, s.data_ptr(), i.data_ptr(),
+                                        poses_out.data_ptr() if poses_out is not None else None, self._stream()),
+                 "zs_merge_topk")
+        return s, i
+
+    def gather_poses(self, poses12: torch.Tensor, idx: torch.Tensor, pose_seg: torch.Tensor, out: torch.Tensor):
+        """Poses of the candidates: out[o][j] = poses12[pose_seg[o].first + idx[o][j] - pose_seg[o].lo] (zeros for
+        idx < 0).  ``idx`` (n_obj,k) int32 global indices, ``pose_seg`` (n_obj,4) int32 {first row, lo, 0, 0}."""
+        n_obj, k = idx.shape
+        self._ck(self.lib.zs_gather_poses(self.h, poses12.data_ptr(), idx.data_ptr(), pose_seg.data_ptr(), n_obj, k,
+                                          out.data_ptr(), self._stream()), "zs_gather_poses")
+        return out
+
+    # fp32-accurate scoring of a handful of hypotheses (the re-rank of the top-k candidates)
+    def features_f32a(self, slot: int, poses12: torch.Tensor, out: torch.Tensor):
+        return self.features(slot, poses12, out=out)[0]
+
+    def pool_f32a(self, wslot: int, feat: torch.Tensor, out: torch.Tensor):
+        return self.pool(wslot, feat, out=out)
+
+    def topk_segments(self, scores: torch.Tensor, segments: torch.Tensor, k: int, index_map: Optional[torch.Tensor] = None,
+                      out=None):
         """Per-segment top-k in one launch.  ``segments``: int32 (n_seg,4) device tensor of {first, count, index_base, 0}.
-        Returns (n_seg,k) scores and indices (index = index_map[first+i] (if given) + index_base)."""
+        Returns (n_seg,k) scores and indices (index = index_map[first+i] (if given) + index_base); ``out`` = (s, i)
+        preallocated outputs."""
         n_seg = segments.shape[0]
-        s = torch.empty((n_seg, k), dtype=torch.float32, device=self.device)
-        i = torch.empty((n_seg, k), dtype=torch.int32, device=self.device)
+        if out is not None:
+            s, i = out
+        else:
+            s = torch.empty((n_seg, k), dtype=torch.float32, device=self.device)
+            i = torch.empty((n_seg, k), dtype=torch.int32, device=self.device)
         self._ck(self.lib.zs_topk_segments(self.h, scores.data_ptr() if scores.numel() else None, segments.data_ptr(), n_seg, k,
                                            index_map.data_ptr() if index_map is not None and index_map.numel() else None,
                                            s.data_ptr(), i.data_ptr(), self._stream()), "zs_topk_segments")

@@ -5,7 +5,16 @@ The reference scores one (object, frame) per ``networkInference`` call and takes
 that over the objects of a frame, returns the per-object top-k by (score desc, hypothesis index
 asc) -- top-1 is exactly the reference's argmax -- and shards hypotheses across the ranks of a
 ``torch.distributed`` group: each rank scores a contiguous slice of every object's hypothesis
-list, and the only data-path collective is one all-gather of k (score, index) records per object.
+list, and the only data-path collective is one all-gather of a per-rank candidate record
+(k scores, indices and poses per object), merged identically on every rank by ``zs_merge_topk``.
+
+With the bf16 tensor-core scorer the k candidates of every object are then re-scored by the
+fp32-accurate scorer (``rerank``) and ordered by that, so the winning hypothesis is the fp32
+argmax of the candidates whatever the GPU count.
+
+PyTorch is plumbing here (device buffers, streams, the process group); every computation inside a
+step is a kernel of libzs.so.  All per-frame device and pinned-host buffers are owned by the
+``FrameScorer`` and reused, so a warmed-up step allocates nothing.
 """
 from __future__ import annotations
 
@@ -15,7 +24,10 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from .engine import ZsContext, get_context, poses_to_rt12
+from .engine import POSE_DTYPES, ZsContext, get_context, poses_to_rt12
+
+MAX_OBJECTS = 64          # ZS_MAX_OBJECTS (include/zs.h): model-cloud slots per context
+MAX_WEIGHT_SLOTS = 4      # ZS_MAX_WEIGHT_SLOTS
 
 
 def shard_range(n: int, rank: int, world: int):
@@ -47,74 +59,102 @@ def spatial_order(points) -> np.ndarray:
     return np.argsort(code, kind="stable")
 
 
-def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k: int):
-    """Merge candidate lists (..., C) -> (..., k) by (score desc, index asc); empty slots are (-inf, -1).
+# ---- candidate records: what one rank contributes to the all-gather ---------------------------------------------
+# int32 [rec_ints]:  n_obj*k score bits | n_obj*k global indices (-1 = empty) | n_obj x {kept by the pre-filter,
+# fallback violation count} | (optional) n_obj*k*12 pose floats of the candidates (for the fp32 re-rank).
+def record_pose_offset(n_obj: int, k: int) -> int:
+    """Offset (in ints) of the pose section: rounded up to 4 ints so that every pose row is 16-byte aligned."""
+    return (2 * n_obj * k + 2 * n_obj + 3) & ~3
 
-    Deterministic and identical on every rank, so top-1 does not depend on the GPU count.
+
+def record_ints(n_obj: int, k: int, with_poses: bool) -> int:
+    return record_pose_offset(n_obj, k) + (12 * n_obj * k if with_poses else 0)
+
+
+def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k: int):
+    """Torch reference of the candidate merge: (..., C) -> (..., k) by (score desc, index asc); empty slots
+    (index < 0) are (-inf, -1); a NaN never beats a real score and is reported as -inf.
+
+    Deterministic and identical on every rank, so top-1 does not depend on the GPU count.  The device path is
+    ``zs_merge_topk`` (one launch); this function is its checker and the CPU (gloo) path.
     """
     s = torch.where(idx < 0, torch.full_like(scores, float("-inf")), scores)
-    s = torch.where(s != s, torch.full_like(s, float("-inf")), s)          # NaN never wins
+    nan = s != s
+    s = torch.where(nan, torch.full_like(s, float("-inf")), s)
     big = torch.iinfo(idx.dtype).max
+    # order: real scores, then NaNs, then empty slots; inside each class (score desc, index asc)
+    cls = torch.where(idx < 0, torch.full_like(idx, 2), torch.where(nan, torch.ones_like(idx), torch.zeros_like(idx)))
     i_key = torch.where(idx < 0, torch.full_like(idx, big), idx)
     o1 = torch.argsort(i_key, dim=-1, stable=True)
-    s1, i1 = torch.gather(s, -1, o1), torch.gather(idx, -1, o1)
+    s1, i1, c1 = torch.gather(s, -1, o1), torch.gather(idx, -1, o1), torch.gather(cls, -1, o1)
     o2 = torch.argsort(-s1, dim=-1, stable=True)
-    s2, i2 = torch.gather(s1, -1, o2), torch.gather(i1, -1, o2)
-    if s2.shape[-1] < k:
-        pad = k - s2.shape[-1]
-        s2 = torch.cat([s2, s2.new_full(s2.shape[:-1] + (pad,), float("-inf"))], -1)
-        i2 = torch.cat([i2, i2.new_full(i2.shape[:-1] + (pad,), -1)], -1)
-    return s2[..., :k].contiguous(), i2[..., :k].contiguous()
+    s2, i2, c2 = torch.gather(s1, -1, o2), torch.gather(i1, -1, o2), torch.gather(c1, -1, o2)
+    o3 = torch.argsort(c2, dim=-1, stable=True)
+    s3, i3 = torch.gather(s2, -1, o3), torch.gather(i2, -1, o3)
+    if s3.shape[-1] < k:
+        pad = k - s3.shape[-1]
+        s3 = torch.cat([s3, s3.new_full(s3.shape[:-1] + (pad,), float("-inf"))], -1)
+        i3 = torch.cat([i3, i3.new_full(i3.shape[:-1] + (pad,), -1)], -1)
+    return s3[..., :k].contiguous(), i3[..., :k].contiguous()
 
 
-def allgather_topk(s: torch.Tensor, i: torch.Tensor, k: int, group=None, ctx: Optional[ZsContext] = None):
-    """(n_obj,k) local candidates on each rank -> merged (n_obj,k), same on every rank.
+def merge_records_reference(gathered: torch.Tensor, n_obj: int, k: int):
+    """Torch/CPU restatement of ``zs_merge_topk`` (include/zs.h) on (world, rec_ints) int32 records, including the
+    never-empty rule applied to the object's whole hypothesis list."""
+    g = gathered.cpu()
+    world = g.shape[0]
+    nk = n_obj * k
+    S = g[:, :nk].contiguous().view(torch.float32).reshape(world, n_obj, k).clone()
+    I = g[:, nk:2 * nk].reshape(world, n_obj, k).clone()
+    info = g[:, 2 * nk:2 * nk + 2 * n_obj].reshape(world, n_obj, 2)
+    for o in range(n_obj):
+        kept = info[:, o, 0] > 0
+        if bool(kept.any()):
+            I[~kept, o, :] = -1                                     # fallback candidates of ranks that kept nothing
+        else:
+            have = [w for w in range(world) if int(I[w, o, 0]) >= 0]
+            best = min(have, key=lambda w: (int(info[w, o, 1]), w)) if have else -1
+            for w in range(world):
+                if w != best:
+                    I[w, o, :] = -1
+    return merge_topk(S.permute(1, 0, 2).reshape(n_obj, world * k), I.permute(1, 0, 2).reshape(n_obj, world * k), k)
 
-    One all-gather of (score bits, index) records, then the merge.  With a ``ctx`` (CUDA tensors) the merge is one
-    launch of the segmented top-k kernel over the (n_obj, world*k) candidates: they are laid out rank-major, every
-    rank's list is already ordered by (score desc, index asc) and ranks own ascending index ranges, so "position
-    ascending" is "global index ascending" among equal scores - the same rule as ``merge_topk``.
-    """
+
+def allgather_records(rec: torch.Tensor, group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One all-gather of this rank's candidate record -> (world, rec_ints), same on every rank."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    if world == 1:
-        return merge_topk(s, i, k)
-    # one record per candidate: score bits and index side by side (indices ship as int32, not as floats)
-    rec = torch.stack([s.to(torch.float32).view(torch.int32), i.to(torch.int32)], dim=-1).contiguous()
+    if out is None:
+        out = torch.empty((world, rec.numel()), dtype=rec.dtype, device=rec.device)
     if rec.is_cuda:
-        out = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
         dist.all_gather_into_tensor(out, rec, group=group)
     else:                                            # gloo (CPU tests) has no all_gather_into_tensor
         parts = [torch.empty_like(rec) for _ in range(world)]
         dist.all_gather(parts, rec, group=group)
-        out = torch.stack(parts)
-    cand = out.permute(1, 0, 2, 3).contiguous()                      # (n_obj, world, k, 2)
+        out.copy_(torch.stack(parts))
+    return out
+
+
+def allgather_topk(s: torch.Tensor, i: torch.Tensor, k: int, group=None, ctx: Optional[ZsContext] = None, info=None):
+    """(n_obj,k) local candidates on each rank -> merged (n_obj,k), same on every rank: one all-gather of the packed
+    record, then the merge (``zs_merge_topk`` with a ``ctx``, else the torch reference)."""
     n_obj = s.shape[0]
-    gs = cand[..., 0].reshape(n_obj, world * k).view(torch.float32)
-    gi = cand[..., 1].reshape(n_obj, world * k)
-    return merge_gathered(gs, gi.to(i.dtype), k, ctx if s.is_cuda else None)
+    if info is None:
+        info = torch.tensor([[1, 0]] * n_obj, dtype=torch.int32, device=s.device)
+    rec = torch.cat([s.to(torch.float32).contiguous().view(torch.int32).reshape(-1), i.to(torch.int32).reshape(-1),
+                     info.to(torch.int32).reshape(-1)])
+    g = allgather_records(rec, group)
+    if ctx is not None and s.is_cuda:
+        S, I = ctx.merge_topk(g, n_obj, k)
+    else:
+        S, I = merge_records_reference(g, n_obj, k)
+    return S, I.to(i.dtype)
 
 
-def merge_gathered(gs: torch.Tensor, gi: torch.Tensor, k: int, ctx: Optional[ZsContext] = None):
-    """Merge rank-major candidate lists (n_obj, world*k) -> (n_obj,k): one segmented top-k launch (``ctx``) or the
-    torch reference ``merge_topk``; both order by (score desc, global index asc) with (-inf, -1) for empty slots."""
-    if ctx is None:
-        return merge_topk(gs, gi, k)
-    n_obj, width = gs.shape
-    gs = torch.where((gi < 0) | (gs != gs), torch.full_like(gs, float("-inf")), gs)       # empty slots and NaN never win
-    S, I = ctx.topk_segments(gs.reshape(-1).contiguous(), _merge_segments(n_obj, width, gs.device), k,
-                             index_map=gi.to(torch.int32).reshape(-1).contiguous())
-    return S, torch.where(S == float("-inf"), torch.full_like(I, -1), I).to(gi.dtype)
-
-
-_seg_cache = {}
-
-
-def _merge_segments(n_obj: int, width: int, device):
-    key = (n_obj, width, str(device))
-    if key not in _seg_cache:
-        _seg_cache[key] = torch.tensor([[o * width, width, 0, 0] for o in range(n_obj)], dtype=torch.int32, device=device)
-    return _seg_cache[key]
+class _Plan:
+    """Everything about a frame that depends only on (hypothesis counts, cloud slots, scorer of each object, rank,
+    world): the row layout of the concatenated hypothesis list and the small device tables.  Cached per shape."""
+    pass
 
 
 class FrameScorer:
@@ -122,32 +162,57 @@ class FrameScorer:
 
     ``weights``: list of folded weight dicts (``weights.fold_state_dict``); ``weight_of(obj_index)``
     picks one per object (the reference keys two YCB-V scorers on object-id parity,
-    online_learning.py:461-463).
+    online_learning.py:461-463).  ``precision``: "bf16" = bf16 features + bf16 tcgen05 scorer (1e-2),
+    "fp32" = fp32-accurate scorer (1e-4).  ``rerank`` (bf16 only, default on): the k candidates of every object are
+    re-scored by the fp32-accurate scorer and ordered by it, which makes the reported top-1 the fp32 argmax of the
+    candidates (python/ossid/scripts/online_learning.py:466-467) at any GPU count.
     """
 
     def __init__(self, weights: Sequence[dict], device: Optional[int] = None, precision: str = "bf16",
                  inconst_ratio_th: float = 100.0, k: int = 8, chunk: int = 32768, group=None,
-                 ctx: Optional[ZsContext] = None, reorder_points: bool = True):
+                 ctx: Optional[ZsContext] = None, reorder_points: bool = True, rerank: Optional[bool] = None):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
+        if len(weights) > MAX_WEIGHT_SLOTS:
+            raise ValueError(f"at most {MAX_WEIGHT_SLOTS} scorers per context, got {len(weights)}")
         if device is None:
             device = torch.cuda.current_device()
         self.ctx = ctx or get_context(device)
         self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
         self.th, self.k, self.chunk, self.group = float(inconst_ratio_th), int(k), int(chunk), group
-        for slot, w in enumerate(weights):
-            self.ctx.set_weights(slot, w)
+        self.rerank = (precision == "bf16") if rerank is None else bool(rerank and precision == "bf16")
+        self._weights = list(weights)
+        self._wtoken = [object() for _ in weights]       # ownership tokens of this scorer's weight slots
         self.n_weights = len(weights)
+        self._sync_weights()
         self.reorder_points = reorder_points
         self._feat = None
         self._pooled = None
         self._scores = None
         self._resident = None
-        self._segments = None
+        self._plan = None
+        self._plans = {}
         self._copy_stream = None
+        self._img_dev = self._depth_dev = None
+        self._raw = [None, None]          # staging of the raw (m,4,4) pose blocks, double-buffered
+        self._raw_free = [None, None]     # event: the pack kernel that last read _raw[b] has run
+        self._p12 = [None, None]
+        self._buf = 0
+        self._pin = {}                    # pinned result ring
+        self._gathered = None
+        self._rr = None                   # re-rank scratch
+        self._result_flat = None          # int32 view over the last result: n_obj*k score bits, then n_obj*k indices
         self._scored = (0, [], 0)     # see last_scored
         self.forced_rank_world = None
         self.stage_events = None     # set to [] to record (stage, units, start_event, end_event) per launch group
+
+    # -- weights ------------------------------------------------------------------------------------
+    def _sync_weights(self):
+        """(Re-)upload this scorer's weights into slots 0..n-1 unless the context still credits them to it: another
+        user of the shared per-device context (a ``PointNet2SSG``, a second ``FrameScorer``) may have taken a slot."""
+        for slot, (w, tok) in enumerate(zip(self._weights, self._wtoken)):
+            if self.ctx.weight_owner.get(slot) is not tok:
+                self.ctx.set_weights(slot, w, owner=tok)
 
     @property
     def last_scored(self) -> int:
@@ -184,84 +249,188 @@ class FrameScorer:
             return dist.get_rank(self.group), dist.get_world_size(self.group)
         return 0, 1
 
+    # -- per-shape plan -----------------------------------------------------------------
+    def _make_plan(self, counts, wslots, npts):
+        rank, world = self._rank_world()
+        key = (tuple(counts), tuple(wslots), tuple(npts), rank, world, self.k)
+        plan = self._plans.get(key)
+        if plan is not None:
+            return plan
+        dev, k, n_obj = self.ctx.device, self.k, len(counts)
+        plan = _Plan()
+        plan.n_obj, plan.rank, plan.world = n_obj, rank, world
+        plan.lo = [shard_range(M, rank, world)[0] for M in counts]
+        plan.m_loc = [shard_range(M, rank, world)[1] - shard_range(M, rank, world)[0] for M in counts]
+        plan.M = list(counts)
+        plan.wslot = list(wslots)
+        # objects laid out by weight slot so that MLP and head run once per scorer over a contiguous row range
+        plan.order = sorted(range(n_obj), key=lambda o: wslots[o])
+        plan.off, total = {}, 0
+        for o in plan.order:
+            plan.off[o] = total
+            total += plan.m_loc[o]
+        plan.total = total
+        to_dev = lambda rows: torch.tensor(rows, dtype=torch.int32).reshape(-1, 4).to(dev)
+        # top-k segments {first score row, count, index base, index-map offset}; candidate poses {first row, lo, 0, 0}
+        plan.seg = to_dev([[plan.off[o], plan.m_loc[o], plan.lo[o], 0] for o in range(n_obj)])
+        plan.pose_seg = to_dev([[plan.off[o], plan.lo[o], 0, 0] for o in range(n_obj)])
+        # re-rank rows: object o's k candidates sit at rows [rr_row[o]*k, +k), objects again grouped by scorer
+        plan.rr_row = {o: r for r, o in enumerate(plan.order)}
+        plan.rr_seg = to_dev([[plan.rr_row[o] * k, k, 0, (o - plan.rr_row[o]) * k] for o in range(n_obj)])
+        plan.rec_ints = record_ints(n_obj, k, self.rerank)
+        plan.pose_at = record_pose_offset(n_obj, k)
+        plan.rec = torch.zeros((plan.rec_ints,), dtype=torch.int32, device=dev)
+        if self.th >= 100:         # no pre-filter: every rank "kept" its hypotheses; with one, zs_filter writes this section
+            plan.rec[2 * n_obj * k: 2 * n_obj * k + 2 * n_obj] = torch.tensor([[1, 0]] * n_obj, dtype=torch.int32).reshape(-1).to(dev)
+        else:                      # device-side pre-filter state: violation counts, kept lists (= the top-k index map) and
+            plan.viol = torch.zeros((max(total, 1),), dtype=torch.int32, device=dev)     # counts (= the segment table)
+            plan.index_map = torch.zeros((max(total, 1),), dtype=torch.int32, device=dev)
+            plan.seg_dyn = plan.seg.clone()
+        plan.out = torch.zeros((2 * n_obj * k,), dtype=torch.int32, device=dev)
+        plan.P = torch.zeros((n_obj, k, 12), dtype=torch.float32, device=dev) if self.rerank else None
+        self._plans[key] = plan
+        return plan
+
     # -- upload (host -> HBM) ---------------------------------------------------------
-    def prefetch_poses(self, objects: List[dict]):
+    def _stage_poses(self, objects: List[dict], plan, buf: int, stream):
+        """Copy this rank's slice of every object's (M,4,4) block into the raw staging buffer ``buf`` on ``stream``
+        (row order = the plan's scorer-grouped layout).  The cast to float32 rows happens on the device."""
+        ctx = self.ctx
+        hosts = [torch.as_tensor(ob["pose_hypos"]) for ob in objects]
+        for t in hosts:
+            if t.ndim != 3 or t.shape[1:] != (4, 4):
+                raise ValueError(f"pose hypotheses must be (M,4,4), got {tuple(t.shape)}")
+        dtype = torch.float32 if all(t.dtype == torch.float32 for t in hosts) else torch.float64
+        raw = self._raw[buf]
+        if raw is None or raw.dtype != dtype or raw.shape[0] < plan.total:
+            cap = max(plan.total, 1) if raw is None or raw.dtype != dtype else max(plan.total, int(raw.shape[0] * 1.25))
+            torch.cuda.current_stream(ctx.device).synchronize()      # growth only: nothing may still read the old block
+            raw = self._raw[buf] = torch.empty((cap, 4, 4), dtype=dtype, device=ctx.device)
+            self._raw_free[buf] = None
+        if self._raw_free[buf] is not None:
+            stream.wait_event(self._raw_free[buf])
+        with torch.cuda.stream(stream):
+            for o, t in enumerate(hosts):
+                if plan.m_loc[o]:
+                    src = t[plan.lo[o]: plan.lo[o] + plan.m_loc[o]]
+                    if src.dtype != dtype:
+                        src = src.to(dtype)
+                    raw[plan.off[o]: plan.off[o] + plan.m_loc[o]].copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return ev
+
+    def prefetch_poses(self, objects: List[dict], weight_of=lambda o: 0):
         """Start the host-to-device copy of this rank's pose slices on a side stream (the poses are >80 % of a frame's
         upload bytes) so that it overlaps the kernels of the frame before; ``upload(..., prefetched=...)`` consumes it."""
-        ctx = self.ctx
-        rank, world = self._rank_world()
+        plan = self._plan_for(objects, weight_of)
         if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=ctx.device)
-        compute = torch.cuda.current_stream(ctx.device)
-        out = []
-        with torch.cuda.stream(self._copy_stream):
-            for ob in objects:
-                lo, hi = shard_range(len(ob["pose_hypos"]), rank, world)
-                p12 = poses_to_rt12(torch.as_tensor(ob["pose_hypos"])[lo:hi], ctx.device)
-                p12.record_stream(compute)              # allocated on the copy stream, read by kernels on the compute stream
-                out.append(p12)
-            ev = torch.cuda.Event()
-            ev.record(self._copy_stream)
-        return out, ev
+            self._copy_stream = torch.cuda.Stream(device=self.ctx.device)
+        buf = self._buf ^ 1
+        ev = self._stage_poses(objects, plan, buf, self._copy_stream)
+        return plan, buf, ev
+
+    def _host_cloud(self, ob):
+        host = ob.get("_zs_host")
+        if host is None:
+            # clouds are static assets (the reference preloads them once, online_learning.py:303-311): keep a
+            # float32, Morton-ordered, pinned host copy so that every frame's upload is one async copy each
+            pts, cols, nrms = (torch.as_tensor(ob[key]).to(torch.float32) for key in
+                               ("model_points", "model_colors", "model_normals"))
+            if self.reorder_points:
+                perm = torch.from_numpy(spatial_order(pts.numpy()))
+                pts, cols, nrms = pts[perm], cols[perm], nrms[perm]
+            host = tuple(t.contiguous().pin_memory() for t in (pts, cols, nrms))
+            ob["_zs_host"] = host
+        return host
+
+    def _plan_for(self, objects, weight_of):
+        if len(objects) > MAX_OBJECTS:
+            raise ValueError(f"a frame may carry at most {MAX_OBJECTS} objects per FrameScorer call (ZS_MAX_OBJECTS), got "
+                             f"{len(objects)}: score it in groups")
+        counts = [len(ob["pose_hypos"]) for ob in objects]
+        wslots = [weight_of(o) % max(self.n_weights, 1) for o in range(len(objects))]
+        npts = [len(ob["model_points"]) for ob in objects]
+        return self._make_plan(counts, wslots, npts)
 
     def upload(self, img_u8, depth, cam_K, objects: List[dict], weight_of=lambda o: 0, prefetched=None):
         """Copy one frame's inputs to the device and keep them resident; this rank's pose slices only."""
         from .zephyr_utils import K2meta
         ctx = self.ctx
-        rank, world = self._rank_world()
+        stream = torch.cuda.current_stream(ctx.device)
         meta = {k: float(v) for k, v in K2meta(np.asarray(cam_K)).items()}
-        ctx.set_frame_u8(img_u8, depth, meta, blur=True)
-        res = []
-        for o, ob in enumerate(objects):
-            slot = o % 64
-            host = ob.get("_zs_host")
-            if host is None:
-                # clouds are static assets (the reference preloads them once, online_learning.py:303-311): keep a
-                # float32, Morton-ordered, pinned host copy so that every frame's upload is one async copy each
-                pts, cols, nrms = (torch.as_tensor(ob[key]).to(torch.float32) for key in
-                                   ("model_points", "model_colors", "model_normals"))
-                if self.reorder_points:
-                    perm = torch.from_numpy(spatial_order(pts.numpy()))
-                    pts, cols, nrms = pts[perm], cols[perm], nrms[perm]
-                host = tuple(t.contiguous().pin_memory() for t in (pts, cols, nrms))
-                ob["_zs_host"] = host
-            pts, cols, nrms = host
-            ctx.set_object(slot, pts, cols, nrms, token=host)      # skipped when this slot already holds this cloud
-            M = len(ob["pose_hypos"])
-            lo, hi = shard_range(M, rank, world)
-            poses12 = prefetched[0][o] if prefetched is not None else \
-                poses_to_rt12(torch.as_tensor(ob["pose_hypos"])[lo:hi], ctx.device)
-            res.append(dict(slot=slot, poses12=poses12, lo=lo, M=M, wslot=weight_of(o) % max(self.n_weights, 1)))
+        # frame: persistent device buffers, two async copies, blur + /255 + HSV on the device
+        img = torch.as_tensor(img_u8)
+        dep = torch.as_tensor(depth)
+        if img.dtype != torch.uint8:
+            raise ValueError("img_u8 must be uint8")
+        if dep.dtype != torch.float32:
+            dep = dep.to(torch.float32)
+        if self._img_dev is None or self._img_dev.shape != img.shape:
+            self._img_dev = torch.empty(img.shape, dtype=torch.uint8, device=ctx.device)
+            self._depth_dev = torch.empty(dep.shape, dtype=torch.float32, device=ctx.device)
+        self._img_dev.copy_(img, non_blocking=True)
+        self._depth_dev.copy_(dep, non_blocking=True)
+        ctx.set_frame_u8(self._img_dev, self._depth_dev, meta, blur=True)
         if prefetched is not None:
-            torch.cuda.current_stream(ctx.device).wait_event(prefetched[1])
-        self._resident = res
-        self._segments = None
-        return res
+            plan, buf, ev = prefetched
+        else:
+            plan = self._plan_for(objects, weight_of)
+            buf = self._buf ^ 1
+            ev = self._stage_poses(objects, plan, buf, stream)
+        for o, ob in enumerate(objects):
+            pts, cols, nrms = host = self._host_cloud(ob)
+            ctx.set_object(o, pts, cols, nrms, token=host)      # skipped when this slot already holds this cloud
+        # one cast kernel over the whole concatenated block: (total,4,4) f32/f64 -> (total,12) f32
+        stream.wait_event(ev)
+        p12 = self._p12[buf]
+        if p12 is None or p12.shape[0] < plan.total:
+            p12 = self._p12[buf] = torch.empty((max(int(plan.total * 1.25), 1), 12), dtype=torch.float32, device=ctx.device)
+        ctx.pack_poses(self._raw[buf][: plan.total], out=p12)
+        done = torch.cuda.Event()
+        done.record(stream)
+        self._raw_free[buf] = done
+        self._buf = buf
+        self._plan = plan
+        self._resident = [dict(slot=o, poses12=p12[plan.off[o]: plan.off[o] + plan.m_loc[o]], lo=plan.lo[o], M=plan.M[o],
+                               wslot=plan.wslot[o]) for o in range(plan.n_obj)]
+        ctx.reserve(min(max(plan.total, plan.n_obj * self.k), 1 << 30))
+        return self._resident
 
     # -- compute (everything resident) --------------------------------------------------
-    def run_resident(self):
+    def run_resident(self, local_record: bool = False):
         """Featurise + score + top-k for the uploaded frame.  Returns (scores (n_obj,k), index (n_obj,k))
-        tensors on the device; indices are global hypothesis indices per object, -1 = empty slot."""
+        tensors on the device; indices are global hypothesis indices per object, -1 = empty slot.
+        ``local_record=True`` (tests that emulate ranks on one device) returns this rank's candidate record instead."""
         ctx, k = self.ctx, self.k
-        res = self._resident
+        res, plan = self._resident, self._plan
+        n_obj, nk = plan.n_obj, plan.n_obj * k
         tensor_cores = self.dtype == torch.bfloat16
+        self._sync_weights()
+        rec = plan.rec
+        S_loc, I_loc = rec[:nk].view(torch.float32).view(n_obj, k), rec[nk:2 * nk].view(n_obj, k)
+        info = rec[2 * nk: 2 * nk + 2 * n_obj]
         # 1. free-space pre-filter per object.  Tensor-core path: the kept count stays on the device (the feature and
         #    MLP kernels read it, zs_set_dynamic_count) and buffers are laid out by capacity, so a filtered frame is as
         #    asynchronous as an unfiltered one.  fp32 parity path: reads back one count per object.
         keeps, n_keeps, n_devs = [], [], []
-        for r in res:
+        filtered = self.th < 100
+        for o, r in enumerate(res):
             keep, n_dev, M = None, None, r["poses12"].shape[0]
-            if self.th < 100 and M > 0:
-                viol = ctx.violations(r["slot"], r["poses12"])
-                if tensor_cores:
-                    keep, n_dev = ctx.filter_async(viol, ctx.obj_npts[r["slot"]], self.th)
-                else:
-                    keep = ctx.filter(viol, ctx.obj_npts[r["slot"]], self.th)
+            if filtered and M > 0:
+                # the kept list lands in the top-k index map and the kept count in the segment table: no glue kernels
+                a = plan.off[o]
+                viol = ctx.violations(r["slot"], r["poses12"], out=plan.viol[a: a + M])
+                keep, n_dev = ctx.filter_async(viol, ctx.obj_npts[r["slot"]], self.th, info=info[2 * o: 2 * o + 2],
+                                               keep_out=plan.index_map[a: a + M],
+                                               n_keep_out=plan.seg_dyn.view(-1)[4 * o + 1: 4 * o + 2])
+                if not tensor_cores:
+                    keep, n_dev = keep[: int(n_dev.item())].clone(), None
             keeps.append(keep)
             n_devs.append(n_dev)
             n_keeps.append(M if (keep is None or n_dev is not None) else keep.shape[0])     # capacity when the count is on the device
-        # 2. objects laid out by weight slot so that the head runs once per scorer over a contiguous range
-        order = sorted(range(len(res)), key=lambda o: res[o]["wslot"])
+        # 2. row layout: the plan's when nothing was compacted on the host, else recomputed from the kept counts
+        order = plan.order
         offs, total = {}, 0
         for o in order:
             offs[o] = total
@@ -269,8 +438,9 @@ class FrameScorer:
         self._scored = (total, [d for d in n_devs if d is not None],
                         sum(n for n, d in zip(n_keeps, n_devs) if d is not None))
         if self._pooled is None or self._pooled.shape[0] < total:
-            self._pooled = torch.zeros((max(total, 1), 1024), dtype=torch.float32, device=ctx.device)
-            self._scores = torch.zeros((max(total, 1),), dtype=torch.float32, device=ctx.device)
+            cap = max(int(total * 1.25), 1)
+            self._pooled = torch.zeros((cap, 1024), dtype=torch.float32, device=ctx.device)
+            self._scores = torch.zeros((cap,), dtype=torch.float32, device=ctx.device)
         # 3. features -> shared MLP + max-pool, chunked so that the feature buffer stays bounded
         same_n = len({ctx.obj_npts[r["slot"]] for r in res}) == 1
         if same_n and all(kp is None for kp in keeps) and total > 0:
@@ -283,11 +453,7 @@ class FrameScorer:
                 lo, hi = offs[members[0]], offs[members[-1]] + n_keeps[members[-1]]
                 for cs in range(lo, hi, self.chunk):
                     ce = min(cs + self.chunk, hi)
-                    need = (ce - cs) * N * 8
-                    if self._feat is None or self._feat.numel() < need or self._feat.dtype != self.dtype:
-                        self._feat = torch.empty((max(need, min(self.chunk, hi - lo) * N * 8),), dtype=self.dtype,
-                                                 device=ctx.device)
-                    feat = self._feat[:need].view(ce - cs, N, 8)
+                    feat = self._feat_buf(ce - cs, N, min(self.chunk, hi - lo))
                     t = self._mark("features", (ce - cs) * N)
                     for o in members:
                         a, b = max(cs, offs[o]), min(ce, offs[o] + n_keeps[o])
@@ -305,11 +471,7 @@ class FrameScorer:
             poses12, N = r["poses12"], ctx.obj_npts[r["slot"]]
             for s in range(0, n_keep, self.chunk):
                 e = min(s + self.chunk, n_keep)
-                need = (e - s) * N * 8
-                if self._feat is None or self._feat.numel() < need or self._feat.dtype != self.dtype:
-                    self._feat = torch.empty((max(need, min(self.chunk, n_keep) * N * 8),), dtype=self.dtype,
-                                             device=ctx.device)
-                feat = self._feat[:need].view(e - s, N, 8)
+                feat = self._feat_buf(e - s, N, min(self.chunk, n_keep))
                 with (ctx.dynamic_count(n_dev, s) if n_dev is not None else contextlib.nullcontext()):
                     t = self._mark("features", (e - s) * N)
                     if keep is None:
@@ -328,35 +490,98 @@ class FrameScorer:
                 t = self._mark("head", hi - lo)
                 ctx.head(ws, self._pooled[lo:hi], tensor_cores, out=self._scores[lo:hi])
                 self._mark(None, 0, t)
-        # 5. per-object top-k in one launch (one CTA per object); indices mapped back to global hypothesis indices
-        #    inside the kernel.  Without a pre-filter the segment table only depends on the uploaded frame and is built
-        #    once per upload; with device-side counts it is assembled on the device (no read-back).
+        # 5. per-object top-k in one launch (one CTA per object), written straight into this rank's candidate record;
+        #    indices mapped back to global hypothesis indices inside the kernel.  Without a pre-filter the segment table
+        #    is the plan's; with device-side counts it is assembled on the device (no read-back).
+        t = self._mark("topk", n_obj)
         if all(kp is None for kp in keeps):
-            if self._segments is None:
-                self._segments = torch.tensor([[offs[o], n_keeps[o], r["lo"], 0] for o, r in enumerate(res)],
-                                              dtype=torch.int32).pin_memory().to(ctx.device, non_blocking=True)
-            S, I = ctx.topk_segments(self._scores, self._segments, k)
+            ctx.topk_segments(self._scores, plan.seg, k, out=(S_loc, I_loc))
         elif all(d is not None or n_keeps[o] == 0 for o, d in enumerate(n_devs)):
-            seg = torch.tensor([[offs[o], 0, r["lo"], 0] for o, r in enumerate(res)], dtype=torch.int32).pin_memory() \
-                .to(ctx.device, non_blocking=True)
-            zero = torch.zeros((1,), dtype=torch.int32, device=ctx.device)
-            seg[:, 1] = torch.cat([d if d is not None else zero for d in n_devs])
-            index_map = torch.zeros((max(total, 1),), dtype=torch.int32, device=ctx.device)
-            for o, d in enumerate(n_devs):
-                if d is not None:
-                    index_map[offs[o]: offs[o] + n_keeps[o]] = keeps[o][: n_keeps[o]]
-            S, I = ctx.topk_segments(self._scores, seg, k, index_map=index_map)
+            ctx.topk_segments(self._scores, plan.seg_dyn, k, index_map=plan.index_map, out=(S_loc, I_loc))
         else:
-            top_s, top_i = [], []
             for o, r in enumerate(res):
                 ts, ti = ctx.topk(self._scores[offs[o]: offs[o] + n_keeps[o]], k, r["lo"], index_map=keeps[o])
-                top_s.append(ts)
-                top_i.append(ti)
-            S, I = torch.stack(top_s), torch.stack(top_i)
+                S_loc[o].copy_(ts)
+                I_loc[o].copy_(ti)
+        if self.rerank:          # the candidates' poses travel with the record: any rank can re-score any candidate
+            ctx.gather_poses(self._p12[self._buf], I_loc, plan.pose_seg, out=rec[plan.pose_at:].view(torch.float32))
+        self._mark(None, 0, t)
+        if local_record:
+            return rec.clone()
+        # 6. multi-GPU: one all-gather of the records, one merge launch; identical on every rank
         rank, world = self._rank_world()
         if world > 1 and self.forced_rank_world is None:
-            S, I = allgather_topk(S, I, k, self.group, ctx=ctx)
+            t = self._mark("allgather+merge", n_obj)
+            if self._gathered is None or self._gathered.shape != (world, plan.rec_ints):
+                self._gathered = torch.empty((world, plan.rec_ints), dtype=torch.int32, device=ctx.device)
+            allgather_records(rec, self.group, out=self._gathered)
+            S, I, P = self.merge_records(self._gathered)
+            self._mark(None, 0, t)
+        else:
+            S, I = S_loc, I_loc
+            P = rec[plan.pose_at:].view(torch.float32).view(n_obj, k, 12) if self.rerank else None
+            self._result_flat = rec[: 2 * nk]
+        if self.rerank:
+            S, I = self._rerank(S, I, P)
         return S, I
+
+    def merge_records(self, gathered: torch.Tensor):
+        """(world, rec_ints) all-gathered records -> merged (S, I, candidate poses or None) on the device."""
+        plan, k = self._plan, self.k
+        n_obj, nk = plan.n_obj, plan.n_obj * k
+        out = plan.out
+        S, I = out[:nk].view(torch.float32).view(n_obj, k), out[nk:].view(n_obj, k)
+        self.ctx.merge_topk(gathered, n_obj, k, out=(S, I), poses_out=plan.P)
+        self._result_flat = out
+        return S, I, plan.P
+
+    def _feat_buf(self, rows: int, N: int, rows_cap: int):
+        need = rows * N * 8
+        if self._feat is None or self._feat.numel() < need or self._feat.dtype != self.dtype:
+            self._feat = torch.empty((max(need, rows_cap * N * 8),), dtype=self.dtype, device=self.ctx.device)
+        return self._feat[:need].view(rows, N, 8)
+
+    def _rerank(self, S, I, P):
+        """Re-score the k candidates of every object with the fp32-accurate scorer and order them by that score
+        ((score desc, index asc) again).  ``P``: (n_obj,k,12) candidate poses; empty slots (I < 0) stay empty."""
+        ctx, plan, k = self.ctx, self._plan, self.k
+        n_obj = plan.n_obj
+        t = self._mark("rerank", n_obj * k)
+        rr = self._rr
+        Nmax = max(ctx.obj_npts[o] for o in range(n_obj))
+        if rr is None or rr["rows"] < n_obj * k or rr["N"] < Nmax:
+            rows = n_obj * k
+            rr = self._rr = dict(rows=rows, N=Nmax,
+                                 feat=torch.zeros((rows * Nmax * 8,), dtype=torch.float32, device=ctx.device),
+                                 pooled=torch.zeros((rows, 1024), dtype=torch.float32, device=ctx.device),
+                                 scores=torch.zeros((rows,), dtype=torch.float32, device=ctx.device),
+                                 out=torch.zeros((2 * rows,), dtype=torch.int32, device=ctx.device))
+        same_n = len({ctx.obj_npts[o] for o in range(n_obj)}) == 1
+        groups = {}
+        for o in plan.order:
+            groups.setdefault(plan.wslot[o], []).append(o)
+        for ws, members in groups.items():
+            r0 = plan.rr_row[members[0]] * k
+            if same_n:
+                N = Nmax
+                feat = rr["feat"][: n_obj * k * N * 8].view(n_obj * k, N, 8)
+                for o in members:
+                    ctx.features_f32a(o, P[o], out=feat[plan.rr_row[o] * k: plan.rr_row[o] * k + k])
+                ctx.pool_f32a(ws, feat[r0: r0 + len(members) * k], out=rr["pooled"][r0: r0 + len(members) * k])
+            else:
+                for o in members:
+                    N = ctx.obj_npts[o]
+                    feat = rr["feat"][: k * N * 8].view(k, N, 8)
+                    ctx.features_f32a(o, P[o], out=feat)
+                    row = plan.rr_row[o] * k
+                    ctx.pool_f32a(ws, feat, out=rr["pooled"][row: row + k])
+            ctx.head(ws, rr["pooled"][r0: r0 + len(members) * k], False, out=rr["scores"][r0: r0 + len(members) * k])
+        nk = n_obj * k
+        S2, I2 = rr["out"][:nk].view(torch.float32).view(n_obj, k), rr["out"][nk: 2 * nk].view(n_obj, k)
+        ctx.topk_segments(rr["scores"], plan.rr_seg, k, index_map=I.reshape(-1), out=(S2, I2))
+        self._result_flat = rr["out"][: 2 * nk]
+        self._mark(None, 0, t)
+        return S2, I2
 
     # -- post-scoring refinement (online_learning.py:471-479) ----------------------------------
     def refine_winners(self, objects: List[dict], I, n_refine: int = 1, icp_max_dist: float = 0.01, max_iter: int = 30):
@@ -393,13 +618,19 @@ class FrameScorer:
         S, I = self.run_resident()
         return S.cpu().numpy(), I.cpu().numpy()
 
+    def _pinned(self, n_ints: int, slot: int):
+        key = (n_ints, slot)
+        if key not in self._pin:
+            self._pin[key] = torch.empty((n_ints,), dtype=torch.int32, pin_memory=True)
+        return self._pin[key]
+
     def score_frames(self, frames: List[dict], weight_of=lambda o: 0, depth: int = 2):
         """Stream of frames (BASELINE.json config 5: multi-frame scoring between finetune steps).
 
         ``frames``: dicts with ``img`` (uint8), ``depth``, ``cam_K``, ``objects``.  Uploads, kernels and the
         read-back of each frame's top-k are all asynchronous; the host only blocks when ``depth`` frames are in
         flight, and the pose hypotheses of frame f+1 (most of a frame's bytes) travel on a side stream while the kernels
-        of frame f run.  Returns a list of
+        of frame f run.  Every device and pinned buffer is owned by this object and reused.  Returns a list of
         ``(scores (n_obj,k), indices (n_obj,k))`` numpy pairs, one per frame.  The free-space pre-filter
         (inconst_ratio_th < 100) keeps its counts on the device on the tensor-core path; only the fp32 parity path
         synchronises once per object to read the kept count.
@@ -408,22 +639,23 @@ class FrameScorer:
         inflight, out = [], []
 
         def drain():
-            ev, s_h, i_h = inflight.pop(0)
+            ev, host, n_obj = inflight.pop(0)
             ev.synchronize()
-            out.append((s_h.numpy().copy(), i_h.numpy().copy()))
+            nk = n_obj * self.k
+            a = host.numpy()
+            out.append((a[:nk].view(np.float32).reshape(n_obj, self.k).copy(), a[nk: 2 * nk].reshape(n_obj, self.k).copy()))
 
-        nxt = self.prefetch_poses(frames[0]["objects"]) if frames else None
+        nxt = self.prefetch_poses(frames[0]["objects"], weight_of) if frames else None
         for f, fr in enumerate(frames):
             self.upload(fr["img"], fr["depth"], fr["cam_K"], fr["objects"], weight_of, prefetched=nxt)
-            nxt = self.prefetch_poses(frames[f + 1]["objects"]) if f + 1 < len(frames) else None    # overlaps this frame's kernels
+            nxt = self.prefetch_poses(frames[f + 1]["objects"], weight_of) if f + 1 < len(frames) else None    # overlaps this frame's kernels
             S, I = self.run_resident()
-            s_h = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
-            i_h = torch.empty(I.shape, dtype=I.dtype, pin_memory=True)
-            s_h.copy_(S, non_blocking=True)
-            i_h.copy_(I, non_blocking=True)
+            n_obj = S.shape[0]
+            host = self._pinned(2 * n_obj * self.k, f % (depth + 1))
+            host.copy_(self._result_flat, non_blocking=True)      # S and I are the two halves of one device buffer
             ev = torch.cuda.Event()
             ev.record(stream)
-            inflight.append((ev, s_h, i_h))
+            inflight.append((ev, host, n_obj))
             if len(inflight) >= depth:
                 drain()
         while inflight:

@@ -150,6 +150,7 @@ class PointNet2SSG(torch.nn.Module):
         self._slot = _next_weight_slot[0] % 4
         _next_weight_slot[0] += 1
         self._uploaded = None
+        self._token = object()
         self.eval()
 
     @property
@@ -163,13 +164,12 @@ class PointNet2SSG(torch.nn.Module):
         return super().load_state_dict(sd, strict=strict)
 
     def _sync_weights(self, ctx):
-        # re-upload when the parameters changed or when another model instance has taken this slot meanwhile
+        # re-upload when the parameters changed or when another user of the context (a model instance, a FrameScorer)
+        # has taken this slot meanwhile: the context credits each slot to the token of its last uploader
         key = (ctx.index, tuple(p._version for p in self.state_dict().values()))
-        owners = ctx.__dict__.setdefault("weight_slot_owner", {})
-        if self._uploaded != key or owners.get(self._slot) != id(self):
-            ctx.set_weights(self._slot, W.fold_state_dict(self.state_dict()))
+        if self._uploaded != key or ctx.weight_owner.get(self._slot) is not self._token:
+            ctx.set_weights(self._slot, W.fold_state_dict(self.state_dict()), owner=self._token)
             self._uploaded = key
-            owners[self._slot] = id(self)
 
     def forward(self, batch):
         if self.training:

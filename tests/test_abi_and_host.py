@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib_path):
         assert hasattr(lib, name), f"{name} declared in include/zs.h but not exported by libzs.so"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes signature table and header disagree"
     bound = _lib.load()
-    assert bound.zs_version() == 100
+    assert bound.zs_version() == 200
     assert bound.zs_strerror(0) == b"ok" and b"CUDA" in bound.zs_strerror(-2)
 
 
@@ -109,6 +109,40 @@ def test_merge_topk_ordering():
     assert mi.tolist() == [[1, 3, 4, 7]] and ms.tolist() == [[5.0, 5.0, 2.0, 1.0]]
     ms, mi = scoring.merge_topk(s[:, :2], i[:, :2], 4)
     assert mi.tolist() == [[3, 7, -1, -1]]
+
+
+def _record(S, I, info):
+    return torch.cat([S.to(torch.float32).contiguous().view(torch.int32).reshape(-1), I.to(torch.int32).reshape(-1),
+                      torch.tensor(info, dtype=torch.int32).reshape(-1)])
+
+
+def test_merge_records_applies_the_never_empty_rule_to_the_whole_list():
+    """ADVICE r1: a rank whose slice was entirely rejected by the pre-filter contributes only its never-empty fallback;
+    that candidate must not enter the merge when another rank kept something, and when NO rank kept anything only the
+    first minimum-violation fallback survives (what a single-GPU run keeps)."""
+    k = 3
+    # object 0: rank 0 kept 2 hypotheses, rank 1 kept none (its fallback scores highest and must still lose)
+    # object 1: no rank kept anything; fallbacks have 9 and 4 violations -> rank 1's survives
+    # object 2: no rank kept anything, equal violation counts -> the lower rank (= lower index) survives
+    S0 = torch.tensor([[1.0, 0.5, float("-inf")], [7.0, float("-inf"), float("-inf")], [2.0, float("-inf"), float("-inf")]])
+    I0 = torch.tensor([[3, 1, -1], [0, -1, -1], [5, -1, -1]])
+    S1 = torch.tensor([[9.0, float("-inf"), float("-inf")], [6.0, float("-inf"), float("-inf")], [8.0, float("-inf"), float("-inf")]])
+    I1 = torch.tensor([[12, -1, -1], [14, -1, -1], [11, -1, -1]])
+    g = torch.stack([_record(S0, I0, [[2, 0], [0, 9], [0, 6]]), _record(S1, I1, [[0, 5], [0, 4], [0, 6]])])
+    S, I = scoring.merge_records_reference(g, 3, k)
+    assert I.tolist() == [[3, 1, -1], [14, -1, -1], [5, -1, -1]]
+    assert S[0, :2].tolist() == [1.0, 0.5] and S[1, 0] == 6.0 and S[2, 0] == 2.0
+    # without the info section saying otherwise ({1,0} = unfiltered), everything merges by score
+    g2 = torch.stack([_record(S0, I0, [[1, 0]] * 3), _record(S1, I1, [[1, 0]] * 3)])
+    S, I = scoring.merge_records_reference(g2, 3, k)
+    assert I.tolist() == [[12, 3, 1], [0, 14, -1], [11, 5, -1]]
+
+
+def test_record_layout_keeps_poses_aligned():
+    for n_obj, k in ((21, 8), (1, 1), (3, 5), (8, 64)):
+        at = scoring.record_pose_offset(n_obj, k)
+        assert at % 4 == 0 and at >= 2 * n_obj * k + 2 * n_obj
+        assert scoring.record_ints(n_obj, k, True) == at + 12 * n_obj * k and scoring.record_ints(n_obj, k, False) == at
 
 
 def _gloo_worker(rank, world, port, q):

@@ -105,8 +105,7 @@ def test_frame_scorer_batched_objects_two_scorers(ctx, precision, rtol):
         es, ei = zo.topk(ref, 5)
         tol = rtol * float(ref.abs().max()) + 1e-6
         np.testing.assert_allclose(S[o, :len(es)], es.numpy(), rtol=0, atol=tol)
-        if len(es) > 1 and float(es[0] - es[1]) > 2 * tol:
-            assert int(I[o, 0]) == int(keep[ei[0]]), f"object {o}: top-1 differs"
+        assert int(I[o, 0]) == int(keep[ei[0]]), f"object {o}: top-1 differs"     # fp32 scorer / fp32 re-rank: unconditional
         assert set(I[o][I[o] >= 0].tolist()) <= set(keep.tolist())
 
 
@@ -134,29 +133,64 @@ def test_features_without_side_outputs_match_oracle(ctx, dtype, rtol, intr, n_pt
     assert torch.equal(hot.float().abs().sum(-1) == 0, aux.float().abs().sum(-1) == 0)
 
 
+def _emulate_ranks(fs, sc, world, wof):
+    """Run `world` emulated ranks on one device and merge their candidate records with zs_merge_topk (+ re-rank)."""
+    recs = []
+    for r in range(world):
+        fs.forced_rank_world = (r, world)
+        fs.upload(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], wof)
+        recs.append(fs.run_resident(local_record=True))
+    S, I, P = fs.merge_records(torch.stack(recs))
+    if fs.rerank:
+        S, I = fs._rerank(S, I, P)
+    S, I = S.cpu().numpy().copy(), I.cpu().numpy().copy()
+    fs.forced_rank_world = None
+    return S, I, recs
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_sharded_scoring_top1_independent_of_gpu_count(ctx, world):
-    """Emulates `world` ranks on one device: each scores its contiguous hypothesis slice, the candidate lists are
+@pytest.mark.parametrize("rerank", [False, True])
+def test_sharded_scoring_top1_independent_of_gpu_count(ctx, world, rerank):
+    """Emulates `world` ranks on one device: each scores its contiguous hypothesis slice, the candidate records are
     merged exactly as after the all-gather; the result must equal the unsharded run (same indices, same scores)."""
     sc = syn.make_scene(29, "lmo", n_obj=3, n_pts=200, n_hypo=257)
     sc["objects"][1]["pose_hypos"][100] = sc["objects"][1]["pose_hypos"][7]      # exact score tie across shards
     ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
-    fs = scoring.FrameScorer(ws, device=0, precision="bf16", inconst_ratio_th=10.0, k=6)
-    S1, I1 = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=lambda o: o % 2)
-    parts_s, parts_i = [], []
-    for r in range(world):
-        fs.forced_rank_world = (r, world)
-        fs.upload(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], lambda o: o % 2)
-        S, I = fs.run_resident()
-        parts_s.append(S)
-        parts_i.append(I)
-    fs.forced_rank_world = None
-    Sm, Im = scoring.merge_topk(torch.cat(parts_s, dim=1), torch.cat(parts_i, dim=1), 6)
-    assert np.array_equal(Im.cpu().numpy(), I1), "sharded top-k indices differ from the single-GPU result"
-    assert np.array_equal(Sm.cpu().numpy(), S1)
+    wof = lambda o: o % 2
+    fs = scoring.FrameScorer(ws, device=0, precision="bf16", inconst_ratio_th=10.0, k=6, rerank=rerank)
+    S1, I1 = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=wof)
+    Sm, Im, recs = _emulate_ranks(fs, sc, world, wof)
+    assert np.array_equal(Im, I1), "sharded top-k indices differ from the single-GPU result"
+    assert np.array_equal(Sm, S1)
+    S_ref, I_ref = scoring.merge_records_reference(torch.stack(recs), 3, 6)       # kernel merge == torch restatement
+    if not rerank:
+        assert np.array_equal(I_ref.numpy(), Im) and np.array_equal(S_ref.numpy(), Sm)
     tie = [int(x) for x in I1[1] if x in (7, 100)]
     if len(tie) == 2:
         assert tie == [7, 100], "tie must resolve to the lower hypothesis index"
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_prefilter_never_empty_rule_is_global(ctx, world):
+    """one shard's slice is rejected entirely by the free-space pre-filter (its never-empty fallback must
+    not reach the merge), and one object is rejected on EVERY shard (exactly the single-GPU fallback must survive)."""
+    sc = syn.make_scene(31, "lmo", n_obj=3, n_pts=200, n_hypo=240)
+    far = np.tile(np.eye(4), (240, 1, 1)); far[:, 2, 3] = 0.05                  # in front of everything: all points violate
+    per = -(-240 // world)
+    sc["objects"][0]["pose_hypos"][per:2 * per] = far[:per]                      # object 0: rank 1's slice is all rejected
+    sc["objects"][2]["pose_hypos"] = far.copy()                                  # object 2: rejected everywhere
+    sc["objects"][2]["pose_hypos"][:, 0, 3] = np.linspace(-0.02, 0.02, 240)      # (different poses, so different counts)
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    wof = lambda o: o % 2
+    for rerank in (False, True):
+        fs = scoring.FrameScorer(ws, device=0, precision="bf16", inconst_ratio_th=10.0, k=5, rerank=rerank)
+        S1, I1 = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=wof)
+        Sm, Im, recs = _emulate_ranks(fs, sc, world, wof)
+        assert np.array_equal(Im, I1) and np.array_equal(Sm, S1), (I1, Im)
+        assert not any(per <= int(i) < 2 * per for i in I1[0]), "a rejected hypothesis reached object 0's top-k"
+        assert (I1[2] >= 0).sum() == 1, "never-empty: exactly one hypothesis of a fully rejected object survives"
+        info = torch.stack(recs)[:, 2 * 3 * 5: 2 * 3 * 5 + 6].reshape(world, 3, 2).cpu()
+        assert int(info[1, 0, 0]) == 0 and int(info[0, 0, 0]) > 0 and int(info[:, 2, 0].sum()) == 0
 
 
 def test_many_model_instances_do_not_share_stale_weights(ctx):
@@ -207,7 +241,7 @@ def test_filtered_frame_with_device_side_counts_equals_the_synchronous_sequence(
     far = np.tile(np.eye(4), (50, 1, 1)); far[:, 2, 3] = 0.05                  # object 2: everything violates free space
     sc["objects"][2]["pose_hypos"] = far
     ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
-    fs = scoring.FrameScorer(ws, device=0, precision="bf16", inconst_ratio_th=10.0, k=6, chunk=256)
+    fs = scoring.FrameScorer(ws, device=0, precision="bf16", inconst_ratio_th=10.0, k=6, chunk=256, rerank=False)
     S, I = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=lambda o: o % 2)
     scored = fs.last_scored
     n_kept = 0
@@ -222,27 +256,87 @@ def test_filtered_frame_with_device_side_counts_equals_the_synchronous_sequence(
 
 
 def test_kernel_merge_of_gathered_candidates_equals_torch_merge(ctx):
-    """The one-launch merge after the all-gather == merge_topk: ties across ranks, empty slots, a NaN, k > valid count."""
+    """The one-launch merge after the all-gather == its torch restatement: ties across ranks, empty slots, a NaN,
+    k > valid count, a genuine -inf score (keeps its index), poses travelling with the winners."""
     g = torch.Generator().manual_seed(11)
     world, k, n_obj = 8, 6, 5
     per = 1000
-    gs, gi = [], []
+    recs = []
+    at = scoring.record_pose_offset(n_obj, k)
     for r in range(world):                                   # every rank: k candidates ordered by (score desc, index asc)
         s = torch.randn(n_obj, per, generator=g)
         s[1, 7] = 5.0                                          # the same top score on every rank of object 1
         if r == 3:
             s[2, :] = float("nan")                             # a rank that only has NaNs for object 2
-        top = torch.stack([torch.tensor(sorted(range(per), key=lambda j: (-float(torch.nan_to_num(s[o, j], nan=-1e30)), j))[:k])
+        if r == 5:
+            s[3, :] = float("-inf")                            # genuine -inf scores: valid hypotheses, lowest rank
+        top = torch.stack([torch.tensor(sorted(range(per), key=lambda j: (-float(torch.nan_to_num(s[o, j], nan=-1e30, neginf=-1e29)), j))[:k])
                            for o in range(n_obj)])
-        gs.append(torch.gather(s, 1, top))
-        gi.append(top + r * per)
-    gs, gi = torch.stack(gs, 1).reshape(n_obj, world * k), torch.stack(gi, 1).reshape(n_obj, world * k).to(torch.int32)
-    gi[4, 3:] = -1                                             # object 4: only three real candidates in total
-    S0, I0 = scoring.merge_topk(gs.to(ctx.device), gi.to(ctx.device), k)
-    S1, I1 = scoring.merge_gathered(gs.to(ctx.device), gi.to(ctx.device), k, ctx)
-    assert torch.equal(I0, I1), (I0, I1)
-    assert torch.equal(S0, S1)
+        gs, gi = torch.gather(s, 1, top), (top + r * per).to(torch.int32)
+        if r > 0:
+            gi[4, :] = -1                                      # object 4: only rank 0 has candidates ...
+        else:
+            gi[4, 3:] = -1                                     # ... and only three of them
+        poses = (gi.to(torch.float32)[..., None] + torch.arange(12) / 16.0)       # recognisable pose rows
+        rec = torch.zeros(scoring.record_ints(n_obj, k, True), dtype=torch.int32)
+        rec[: n_obj * k] = gs.contiguous().view(torch.int32).reshape(-1)
+        rec[n_obj * k: 2 * n_obj * k] = gi.reshape(-1)
+        rec[2 * n_obj * k: 2 * n_obj * k + 2 * n_obj] = torch.tensor([[1, 0]] * n_obj, dtype=torch.int32).reshape(-1)
+        rec[at:] = poses.contiguous().view(torch.int32).reshape(-1)
+        recs.append(rec)
+    gathered = torch.stack(recs)
+    S0, I0 = scoring.merge_records_reference(gathered, n_obj, k)
+    P1 = torch.zeros(n_obj, k, 12, device=ctx.device)
+    S1, I1 = ctx.merge_topk(gathered.to(ctx.device), n_obj, k, poses_out=P1)
+    assert torch.equal(I0, I1.cpu()), (I0, I1)
+    assert torch.equal(S0, S1.cpu())
     assert I1[1, :3].tolist() == [7, 1007, 2007] and I1[4, 3:].tolist() == [-1, -1, -1]
+    exp_p = torch.where(I1.cpu()[..., None] >= 0, I1.cpu().to(torch.float32)[..., None] + torch.arange(12) / 16.0, torch.zeros(1))
+    assert torch.equal(P1.cpu(), exp_p)
+    S2, I2 = ctx.merge_topk(gathered.to(ctx.device), n_obj, k)                  # without the pose output
+    assert torch.equal(I2, I1) and torch.equal(S2, S1)
+
+
+def test_pack_poses_equals_host_cast(ctx):
+    """zs_pack_poses: (n,4,4) float64 / float32 -> (n,12) float32, the single cast of the hand-over, bit for bit."""
+    from ossid_code_b200.engine import poses_to_rt12
+    g = torch.Generator().manual_seed(3)
+    T = torch.randn(1001, 4, 4, generator=g, dtype=torch.float64) * 3.0
+    for src in (T, T.to(torch.float32)):
+        got = poses_to_rt12(src, ctx.device).cpu()
+        assert torch.equal(got, src[:, :3, :4].to(torch.float32).reshape(-1, 12))
+    assert poses_to_rt12(T[:0], ctx.device).shape == (0, 12)
+
+
+def test_frame_scorer_and_shim_models_do_not_clobber_each_others_weights(ctx):
+    """FrameScorer and PointNet2SSG share the per-device context's weight slots; each must re-upload when
+    the other has taken its slot, in both directions."""
+    from ossid_code_b200 import zephyr_shim
+    sc = syn.make_scene(19, "lmo", n_obj=2, n_pts=128, n_hypo=60)
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    fs = scoring.FrameScorer(ws, device=0, precision="bf16", k=4)
+    S0, I0 = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=lambda o: o % 2)
+    x = (torch.randn(5, 64, 8, generator=torch.Generator().manual_seed(0)) * 0.5).to(ctx.device)
+    models = []
+    for seed in (7, 8, 9, 10):                                    # four models: every slot of the context gets taken
+        m = zephyr_shim.PointNet2SSG(8, None, 1)
+        m.load_state_dict(weights.seeded_state_dict(seed))
+        models.append((m.to(0).eval(), zo.scorer(x.cpu(), weights.seeded_folded(seed))))
+    for m, ref in models:
+        got = m({"point_x": x}).reshape(-1).cpu()
+        assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-6
+    S1, I1 = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=lambda o: o % 2)
+    assert np.array_equal(S0, S1) and np.array_equal(I0, I1), "FrameScorer scored with a shim model's weights"
+    for m, ref in models:                                         # and the models re-upload after the FrameScorer ran
+        got = m({"point_x": x}).reshape(-1).cpu()
+        assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-6
+
+
+def test_more_objects_than_cloud_slots_raises(ctx):
+    sc = syn.make_scene(19, "tiny", n_obj=1, n_pts=32, n_hypo=4)
+    fs = scoring.FrameScorer([weights.seeded_folded(0)], device=0, k=2)
+    with pytest.raises(ValueError, match="at most 64 objects"):
+        fs.upload(sc["img"], sc["depth"], sc["cam_K"], [sc["objects"][0]] * 65)
 
 
 @pytest.mark.parametrize("chunk", [96, 32768])

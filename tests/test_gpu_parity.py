@@ -227,7 +227,10 @@ def test_networkInference_drop_in_matches_reference_fixture(golden_dir, precisio
     rtol = SCORE_F32_RTOL if precision == "fp32" else SCORE_BF16_RTOL
     assert np.abs(scores - ref_scores).max() <= rtol * np.abs(ref_scores).max() + 1e-6
     order = np.sort(ref_scores)[::-1]
-    if order[0] - order[1] > 2 * rtol * np.abs(ref_scores).max():
+    # fp32-accurate scorer: the winner is the reference's winner, unconditionally.  The bf16 scorer behind this
+    # single-object API only sees bf16 features (1e-2 contract): its winner is checked when the margin exceeds that
+    # tolerance (FrameScorer, which owns the poses, re-ranks its candidates in fp32 instead: test_full_c2_frame_top1).
+    if precision == "fp32" or order[0] - order[1] > 2 * rtol * np.abs(ref_scores).max():
         assert int(scores.argmax()) == int(ref_scores.argmax()), "top-1 hypothesis differs"
 
 
@@ -242,10 +245,53 @@ def test_frame_scorer_top1_matches_oracle_fp32(ctx):
         ref = zo.scorer(f["point_x"][keep], w)
         es, ei = zo.topk(ref, 4)
         exp_idx = keep[ei].tolist()
-        margin = float(es[0] - es[1]) if len(es) > 1 else 1.0
-        if margin > 2 * SCORE_F32_RTOL * float(ref.abs().max()):
-            assert int(I[o, 0]) == exp_idx[0], f"object {o}: top-1 differs"
+        assert int(I[o, 0]) == exp_idx[0], f"object {o}: top-1 differs"
         np.testing.assert_allclose(S[o, :len(es)], es.numpy(), rtol=0, atol=_score_tol(ref, SCORE_F32_RTOL) + 1e-6)
+
+
+def test_full_c2_frame_top1_is_the_fp32_argmax(ctx):
+    """BASELINE.json configs[1] at full size (21 objects x 10,000 hypotheses x 1,000 points), bf16 tensor-core scorer +
+    fp32-accurate re-rank: for EVERY object the reported top-1 is the argmax of the fp32 oracle evaluated on the GPU's
+    8 candidates plus 256 random hypotheses of that object (online_learning.py:466-467), with no margin guard."""
+    import cv2
+    sc = syn.make_scene(1, "ycbv", n_obj=21, n_pts=1000, n_hypo=10000)
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    fs = scoring.FrameScorer(ws, device=0, precision="bf16", k=8)
+    assert fs.rerank
+    S, I = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=lambda o: o % 2)
+    img01 = cv2.GaussianBlur(sc["img"], (5, 5), 0) / 255.
+    meta = glue.K2meta(sc["cam_K"])
+    rng = np.random.default_rng(5)
+    for o, ob in enumerate(sc["objects"]):
+        cand = sorted(set(int(i) for i in I[o] if i >= 0) | set(rng.choice(10000, 256, replace=False).tolist()))
+        f = zo.features(img01, sc["depth"], ob["pose_hypos"][cand], meta, ob["model_points"], ob["model_colors"],
+                        ob["model_normals"])
+        ref = zo.scorer(f["point_x"], ws[o % 2])
+        best = cand[int(torch.argmax(ref))]
+        assert int(I[o, 0]) == best, f"object {o}: GPU top-1 {int(I[o, 0])} != fp32 oracle argmax {best}"
+        assert abs(float(S[o, 0]) - float(ref.max())) <= SCORE_F32_RTOL * float(ref.abs().max()) + 1e-6
+        assert all(S[o, j] >= S[o, j + 1] for j in range(7))
+
+
+def test_reference_glue_drives_the_gpu_path_when_present(ctx, golden_dir):
+    """The reference's own, unmodified networkInference (python/ossid/utils/zephyr_utils.py:10-47) on top of the shim.
+    Needs /root/reference AND a GPU in one place; skipped wherever either is missing (the mirror is tested above)."""
+    if not os.path.exists("/root/reference/python/ossid/utils/zephyr_utils.py"):
+        pytest.skip("/root/reference is not on this machine")
+    from oracle import gen_golden
+    ref_glue = gen_golden.import_reference(zephyr_shim.projectPointsUv)
+    g = np.load(os.path.join(golden_dir, "network_inference.npz"))
+    args = type("Args", (), dict(inconst_ratio_th=10.0, zs_precision="fp32"))()
+    ds = zephyr_shim.ScoreDataset([], "", "lmo", args, mode="test")
+    ds.gpu_frontend = False                                   # the reference glue hands over the blurred float image
+    model = zephyr_shim.PointNet2SSG(ds.dim_point, args, num_class=1)
+    model.load_state_dict(weights.seeded_state_dict(int(g["weight_seed"])))
+    model = model.to(0).eval()
+    data = dict(img=g["img"], depth=g["depth"], cam_K=g["cam_K"], model_colors=g["model_colors"],
+                model_points=g["model_points"], model_normals=g["model_normals"], pose_hypos=g["pose_hypos"].copy())
+    poses, scores, errs, uv = ref_glue.networkInference(model, ds, data)
+    assert np.array_equal(poses, g["th10_poses"])
+    assert int(np.asarray(scores).argmax()) == int(g["th10_scores"].argmax())
 
 
 # --- full-size, size-independent properties (BASELINE.json configs[1] shape) -------------------------
