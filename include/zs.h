@@ -144,32 +144,41 @@ ZS_API int zs_filter(zs_ctx* ctx, const int32_t* viol, int n, int n_pts, float i
 ZS_API int zs_set_dynamic_count(zs_ctx* ctx, const int32_t* n_dev, int n_offset);
 
 /* Second half of getPointNetData: features for hypotheses keep_idx[0..n_keep) of `poses`
- * (keep_idx NULL = all of 0..n_keep).  feat_out [dev] [n_keep][n_pts][8] float32 or bf16;
+ * (keep_idx NULL = all of 0..n_keep).  feat_out [dev] [n_keep][n_pts][8] float32 or bf16, or for ZS_BF16_SPLIT
+ * [n_keep][2][n_pts][8] bf16 = per hypothesis a plane of bf16(x) and a plane of bf16(x - bf16(x)) (no side outputs
+ * with that format);
  * uv_out [dev] int32 [n_keep][n_pts][2] (nullable); mask_out [dev] uint8 [n_keep][n_pts]
  * (nullable); viol_out [dev] int32 [n_keep] (nullable). */
 ZS_API int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const int32_t* keep_idx, int n_keep,
                 void* feat_out, int feat_dtype, int32_t* uv_out, uint8_t* mask_out,
                 int32_t* viol_out, void* stream);
 
-/* Scorer forward, `model({"point_x": point_x})` (zephyr_utils.py:34).  feat [dev]
- * [n][n_pts][8] in feat_dtype.  precision ZS_F32: CUDA-core fp32 path (feat float32);
- * ZS_BF16: tcgen05 tensor-core path (feat bf16).  scores_out [dev] float32 [n]. */
+/* Scorer forward, `model({"point_x": point_x})` (zephyr_utils.py:34).  feat [dev] [n][n_pts][8] in feat_dtype
+ * ([n][2][n_pts][8] bf16 for ZS_BF16_SPLIT).  precision ZS_BF16 (feat ZS_BF16): bf16 tcgen05 path, 1e-2;
+ * precision ZS_F32: fp32-accurate, 1e-4 -- feat ZS_BF16_SPLIT: tcgen05 with 3-term bf16-split products and the fp32
+ * head; feat ZS_F32: the CUDA-core fp32 kernel (reference implementation of the same arithmetic).
+ * scores_out [dev] float32 [n]. */
 ZS_API int zs_score(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtype, int n, int n_pts,
              int precision, float* scores_out, void* stream);
 
+/* point_x handed over as float32 (the reference's dtype at zephyr_utils.py:34) -> the split-bf16 planes the fp32-accurate
+ * tensor-core scorer reads: feat [dev] float32 [n][n_pts][8] -> split_out [dev] bf16 [n][2][n_pts][8]. */
+ZS_API int zs_split_features(zs_ctx* ctx, const float* feat, int n, int n_pts, void* split_out, void* stream);
+
 /* The two halves of zs_score, exposed so that callers can keep the pooled vectors and so that
  * each stage can be timed alone: zs_pool = shared per-point MLP + max over points
- * (pooled_out [dev] float32 [n][1024]); zs_head = 1024 -> 512 -> 256 -> 1, precision ZS_F32: fp32 on
+ * (pooled_out [dev] float32 [n][1024]; feat_dtype ZS_F32 / ZS_BF16 / ZS_BF16_SPLIT picks the kernel as in zs_score);
+ * zs_head = 1024 -> 512 -> 256 -> 1, precision ZS_F32: fp32 on
  * CUDA cores (1e-4 parity path), ZS_BF16: tf32 tensor cores (what zs_score uses after the bf16 MLP). */
 ZS_API int zs_pool(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtype, int n, int n_pts,
             float* pooled_out, void* stream);
 ZS_API int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n, int precision, float* scores_out,
             void* stream);
 
-/* Diagnostic twin of zs_pool for bf16 features: additionally dumps the bf16-rounded activations
- * of layers 1 and 2 (h1_out [dev] float32 [n*n_pts][64], h2_out [dev] float32 [n*n_pts][128];
+/* Diagnostic twin of zs_pool for ZS_BF16 / ZS_BF16_SPLIT features: additionally dumps the activations of layers 1
+ * and 2 as the next layer reads them (h1_out [dev] float32 [n*n_pts][64], h2_out [dev] float32 [n*n_pts][128];
  * either may be NULL).  Used by the parity tests to localise a tensor-core mismatch. */
-ZS_API int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat_bf16, int n, int n_pts, float* pooled_out,
+ZS_API int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtype, int n, int n_pts, float* pooled_out,
                   float* h1_out, float* h2_out, void* stream);
 
 /* Per-object top-k, ordered by (score desc, index asc); k <= ZS_MAX_TOPK.  Generalises

@@ -36,9 +36,10 @@ SIGNATURES = {
     "zs_gather_poses": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "zs_features": (_i, [_p, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
     "zs_score": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p]),
+    "zs_split_features": (_i, [_p, _p, _i, _i, _p, _p]),
     "zs_pool": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "zs_head": (_i, [_p, _i, _p, _i, _i, _p, _p]),
-    "zs_pool_debug": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p]),
+    "zs_pool_debug": (_i, [_p, _i, _p, _i, _i, _i, _p, _p, _p, _p]),
     "zs_pose_errors": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _p]),
     "zs_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "zs_topk_segments": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),

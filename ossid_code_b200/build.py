@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzs.so")
 STAMP = os.path.join(HERE, "libzs.so.stamp")
-SOURCES = ("zs_api.cu", "zs_features.cu", "zs_score_f32.cu", "zs_score_tc.cu", "zs_head_tc.cu", "zs_topk.cu", "zs_metrics.cu", "zs_icp.cu")
+SOURCES = ("zs_api.cu", "zs_features.cu", "zs_score_f32.cu", "zs_score_tc.cu", "zs_score_tc3.cu", "zs_head_tc.cu", "zs_topk.cu", "zs_metrics.cu", "zs_icp.cu")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

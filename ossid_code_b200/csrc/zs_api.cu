@@ -109,7 +109,7 @@ extern "C" void zs_destroy(zs_ctx* ctx) {
     zs_tc_destroy(ctx);
     cudaFree(ctx->frame.packed);
     for (auto& o : ctx->obj) { cudaFree(o.pA); cudaFree(o.pB); cudaFree(o.pV); }
-    for (auto& w : ctx->w) { cudaFree(w.f32); cudaFree(w.f32t); cudaFree(w.bf16); }
+    for (auto& w : ctx->w) { cudaFree(w.f32); cudaFree(w.f32t); cudaFree(w.bf16); cudaFree(w.bf16x2); }
     cudaFree(ctx->ws);
     cudaFree(ctx->lut255);
     delete ctx;
@@ -284,6 +284,8 @@ extern "C" int zs_set_weights(zs_ctx* ctx, int slot, const float* blob, size_t n
     int rc = zs_f32_prepare_weights(ctx, slot, st);
     if (rc) return rc;
     rc = zs_tc_prepare_weights(ctx, slot, st);
+    if (rc) return rc;
+    rc = zs_tc3_prepare_weights(ctx, slot, st);
     if (rc) return rc;
     w.set = true;
     return ZS_OK;

@@ -33,6 +33,7 @@ struct zs_weights {
     float* f32 = nullptr;            // ZS_WEIGHT_FLOATS, layout of zs_set_weights
     float* f32t = nullptr;           // transposed ([K][CO]) copies of W1 W2 W3 F1 F2 (zs_score_f32.cu)
     __nv_bfloat16* bf16 = nullptr;   // tensor-core operand images of W1..W3 (see zs_score_tc.cu)
+    __nv_bfloat16* bf16x2 = nullptr; // the same as bf16 hi + lo pairs for the fp32-accurate kernel (zs_score_tc3.cu)
     bool set = false;
 };
 
@@ -69,6 +70,9 @@ int zs_reserve_ws(zs_ctx* ctx, size_t bytes);
 int zs_tc_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);   // zs_score_tc.cu
 void zs_tc_destroy(zs_ctx* ctx);
 int zs_score_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, int n_pts, float* pooled, cudaStream_t st);
+int zs_tc3_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);  // zs_score_tc3.cu
+int zs_score_tc3(zs_ctx* ctx, int slot, const void* feat_split, int n, int n_pts, float* pooled, float* dbg_h1, float* dbg_h2,
+                 cudaStream_t st);
 int zs_head_tc(zs_ctx* ctx, int slot, const float* pooled, int n, float* scores, float* g1, cudaStream_t st);  // zs_head_tc.cu
 int zs_f32_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);  // zs_score_f32.cu
 

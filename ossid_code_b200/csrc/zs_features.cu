@@ -40,6 +40,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// (a, b) -> bf16x2 of the high parts and bf16x2 of the remainders: x = hi + lo to 16 mantissa bits
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
 // fp32 features: a lane holds 32 contiguous bytes of its point, so a direct store would write two
 // half-filled 32-byte sectors per lane.  Stage the warp's 32 x 32 B through shared memory and write
 // two fully contiguous 512-byte warp stores instead.  `n_act` = points of this warp-iteration.
@@ -217,7 +223,9 @@ __device__ __forceinline__ void st_f32_row(float* p, float4 lo, float4 hi, bool 
     }
 }
 
-template <bool kBf16, bool kSmem>
+// kFmt: ZS_F32 (32-byte rows), ZS_BF16 (16-byte rows) or ZS_BF16_SPLIT (per hypothesis a plane of bf16(x) rows followed by
+// a plane of bf16(x - bf16(x)) rows: the two K halves of the fp32-accurate scorer's layer-1 operand, zs_score_tc3.cu).
+template <int kFmt, bool kSmem>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
                   const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out, int aligned32,
@@ -281,12 +289,21 @@ zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, cons
                 const float c = dot * rsqrt_fast(fmaf(x[j], x[j], fmaf(y[j], y[j], z[j] * z[j]))) *
                                 rsqrt_fast(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
                 const float f6 = (fabsf(c) <= kFltMax) ? c : 0.f;      // NaN / inf (degenerate pose) -> 0
-                if (kBf16) {
+                if (kFmt == ZS_BF16) {
                     uint4 v;
                     v.x = pack_bf16x2(f0, f1); v.y = pack_bf16x2(dH, f3);
                     v.z = pack_bf16x2(f4, f5); v.w = pack_bf16x2(f6, 0.f);
                     if (!valid[j]) v = make_uint4(0u, 0u, 0u, 0u);
                     if (p < p_end) st_cs_u4(reinterpret_cast<uint4*>(feat_out) + row + p, v);
+                } else if (kFmt == ZS_BF16_SPLIT) {
+                    uint4 h, l;
+                    split_bf16x2(f0, f1, h.x, l.x); split_bf16x2(dH, f3, h.y, l.y);
+                    split_bf16x2(f4, f5, h.z, l.z); split_bf16x2(f6, 0.f, h.w, l.w);
+                    if (!valid[j]) h = l = make_uint4(0u, 0u, 0u, 0u);
+                    if (p < p_end) {
+                        st_cs_u4(reinterpret_cast<uint4*>(feat_out) + 2 * row + p, h);
+                        st_cs_u4(reinterpret_cast<uint4*>(feat_out) + 2 * row + N + p, l);
+                    }
                 } else {
                     float4 lo = make_float4(f0, f1, dH, f3), hi = make_float4(f4, f5, f6, 0.f);
                     if (!valid[j]) lo = hi = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -501,8 +518,10 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
     if (ctx && n_keep == 0) return ZS_OK;
     int rc = check_obj(ctx, obj_slot, poses, o, cam);
     if (rc) return rc;
-    if (n_keep < 0 || (feat_dtype != ZS_F32 && feat_dtype != ZS_BF16))
+    if (n_keep < 0 || (feat_dtype != ZS_F32 && feat_dtype != ZS_BF16 && feat_dtype != ZS_BF16_SPLIT))
         return zs_fail(ctx, ZS_ERR_INVALID, "n_keep %d, feat_dtype %d", n_keep, feat_dtype);
+    if (feat_dtype == ZS_BF16_SPLIT && (uv_out || mask_out || viol_out))
+        return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "split-bf16 features have no side outputs: request them with ZS_F32 features");
     if (!feat_out || ((uintptr_t)feat_out & 15) || (uv_out && ((uintptr_t)uv_out & 7)))
         return zs_fail(ctx, ZS_ERR_INVALID, "feat_out must be 16-byte aligned (uv_out 8)");
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -515,25 +534,26 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
     const int grid = grid_for(ctx, units, cs.ctas_per_sm, threads / 32);
     cudaStream_t st = (cudaStream_t)stream;
     const float4* frame = ctx->frame.packed;
-#define ZS_LAUNCH_FEAT(BF, SM)                                                                          \
+#define ZS_LAUNCH_FEAT(FMT, SM)                                                                         \
     do {                                                                                                \
         if (aux) {                                                                                      \
-            rc = opt_in_smem(ctx, zs_k_features<BF, SM, true>, smem);                          \
+            rc = opt_in_smem(ctx, zs_k_features<(FMT) == ZS_BF16, SM, true>, smem);                     \
             if (rc) return rc;                                                                          \
-            zs_k_features<BF, SM, true><<<grid, threads, smem, st>>>(                         \
+            zs_k_features<(FMT) == ZS_BF16, SM, true><<<grid, threads, smem, st>>>(                     \
                 o, cam, frame, poses, keep_idx, n_keep, feat_out, uv_out, mask_out, viol_out,           \
                 ctx->dyn_n, ctx->dyn_off);                                                              \
         } else {                                                                                        \
-            rc = opt_in_smem(ctx, zs_k_features_hot<BF, SM>, smem);                            \
+            rc = opt_in_smem(ctx, zs_k_features_hot<FMT, SM>, smem);                                    \
             if (rc) return rc;                                                                          \
-            zs_k_features_hot<BF, SM><<<grid, threads, smem, st>>>(o, cam, frame, poses,      \
-                                                                  keep_idx, n_keep, feat_out,          \
-                                                                  (((uintptr_t)feat_out & 31) == 0),   \
-                                                                  ctx->dyn_n, ctx->dyn_off);           \
+            zs_k_features_hot<FMT, SM><<<grid, threads, smem, st>>>(o, cam, frame, poses,               \
+                                                                   keep_idx, n_keep, feat_out,          \
+                                                                   (((uintptr_t)feat_out & 31) == 0),   \
+                                                                   ctx->dyn_n, ctx->dyn_off);           \
         }                                                                                               \
     } while (0)
-    if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_FEAT(true, true); else ZS_LAUNCH_FEAT(true, false); }
-    else                       { if (in_smem) ZS_LAUNCH_FEAT(false, true); else ZS_LAUNCH_FEAT(false, false); }
+    if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_FEAT(ZS_BF16, true); else ZS_LAUNCH_FEAT(ZS_BF16, false); }
+    else if (feat_dtype == ZS_BF16_SPLIT) { if (in_smem) ZS_LAUNCH_FEAT(ZS_BF16_SPLIT, true); else ZS_LAUNCH_FEAT(ZS_BF16_SPLIT, false); }
+    else                       { if (in_smem) ZS_LAUNCH_FEAT(ZS_F32, true); else ZS_LAUNCH_FEAT(ZS_F32, false); }
 #undef ZS_LAUNCH_FEAT
     ZS_LAUNCHED(ctx);
     return ZS_OK;

@@ -238,6 +238,7 @@ static int pool_impl(zs_ctx* ctx, int slot, const void* feat, int feat_dtype, in
         ZS_LAUNCHED(ctx);
         return ZS_OK;
     }
+    if (feat_dtype == ZS_BF16_SPLIT) return zs_score_tc3(ctx, slot, feat, m, n_pts, pooled, nullptr, nullptr, st);
     return zs_score_tc(ctx, slot, (const __nv_bfloat16*)feat, m, n_pts, pooled, st);
 }
 
@@ -246,7 +247,8 @@ static int score_args(zs_ctx* ctx, int weight_slot, const void* feat, int feat_d
     if (weight_slot < 0 || weight_slot >= ZS_MAX_WEIGHT_SLOTS || !ctx->w[weight_slot].set)
         return zs_fail(ctx, ZS_ERR_STATE, "weight slot %d not set", weight_slot);
     if (n < 0 || n_pts <= 0) return zs_fail(ctx, ZS_ERR_INVALID, "n %d n_pts %d", n, n_pts);
-    if (feat_dtype != ZS_F32 && feat_dtype != ZS_BF16) return zs_fail(ctx, ZS_ERR_INVALID, "feat_dtype %d", feat_dtype);
+    if (feat_dtype != ZS_F32 && feat_dtype != ZS_BF16 && feat_dtype != ZS_BF16_SPLIT)
+        return zs_fail(ctx, ZS_ERR_INVALID, "feat_dtype %d", feat_dtype);
     if (n > 0 && (!feat || ((uintptr_t)feat & 15))) return zs_fail(ctx, ZS_ERR_INVALID, "feat must be non-null, 16-byte aligned");
     return ZS_OK;
 }
@@ -287,7 +289,7 @@ extern "C" int zs_score(zs_ctx* ctx, int weight_slot, const void* feat, int feat
                         int precision, float* scores_out, void* stream) {
     int rc = score_args(ctx, weight_slot, feat, feat_dtype, n, n_pts);
     if (rc) return rc;
-    if (precision != feat_dtype)
+    if (precision != feat_dtype && !(precision == ZS_F32 && feat_dtype == ZS_BF16_SPLIT))
         return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "precision %d needs matching feature dtype (got %d)", precision, feat_dtype);
     if (ctx->dyn_n) return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "device-side counts: use zs_pool + zs_head");
     if (n == 0) return ZS_OK;
@@ -300,7 +302,7 @@ extern "C" int zs_score(zs_ctx* ctx, int weight_slot, const void* feat, int feat
     float* pooled = (float*)ctx->ws;
     float* g1 = pooled + (size_t)chunk * 1024;
     float* g2 = g1 + (size_t)chunk * 512;
-    const size_t esz = feat_dtype == ZS_F32 ? 4 : 2;
+    const size_t esz = feat_dtype == ZS_BF16 ? 2 : 4;          // ZS_BF16_SPLIT: two bf16 planes = 32 bytes per point as well
     for (int s = 0; s < n; s += chunk) {
         const int m = (n - s) < chunk ? (n - s) : chunk;
         rc = pool_impl(ctx, weight_slot, (const char*)feat + (size_t)s * n_pts * 8 * esz, feat_dtype, m, n_pts, pooled, st);

@@ -35,7 +35,6 @@
 #include <cuda.h>
 
 #include "zs_common.cuh"
-#include "zs_tc.cuh"
 
 namespace {
 
@@ -56,6 +55,10 @@ constexpr bool kDbgDump = true;
 #define PROF_WAIT(slot, stmt) stmt
 #define PROF_DUMP(base, cnt)
 #endif
+
+}  // namespace
+#include "zs_tc.cuh"     // after EXP(): the shared epilogue helpers honour the profiling build's experiment bits
+namespace {
 
 constexpr int kTile = 128;               // points per CTA per pair-tile
 constexpr int kPairTile = 2 * kTile;     // points per pair-tile
@@ -436,13 +439,17 @@ int zs_score_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, int n_p
     return launch_tc(ctx, slot, feat, n, n_pts, pooled, nullptr, nullptr, st);
 }
 
-// Diagnostic entry point: as zs_pool (bf16) but also dumps the bf16-rounded activations of layers 1 and 2.
-extern "C" int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat_bf16, int n, int n_pts, float* pooled_out,
+// Diagnostic entry point: as zs_pool (bf16 or split-bf16 features) but also dumps the activations of layers 1 and 2 as
+// the next layer reads them (bf16-rounded; hi + lo for the split kernel).
+extern "C" int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtype, int n, int n_pts, float* pooled_out,
                              float* h1_out, float* h2_out, void* stream) {
     if (!ctx) return ZS_ERR_INVALID;
     if (weight_slot < 0 || weight_slot >= ZS_MAX_WEIGHT_SLOTS || !ctx->w[weight_slot].set)
         return zs_fail(ctx, ZS_ERR_STATE, "weight slot %d not set", weight_slot);
-    if (n <= 0 || n_pts <= 0 || !feat_bf16 || !pooled_out) return zs_fail(ctx, ZS_ERR_INVALID, "zs_pool_debug arguments");
+    if (n <= 0 || n_pts <= 0 || !feat || !pooled_out || (feat_dtype != ZS_BF16 && feat_dtype != ZS_BF16_SPLIT))
+        return zs_fail(ctx, ZS_ERR_INVALID, "zs_pool_debug arguments");
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
-    return launch_tc(ctx, weight_slot, (const __nv_bfloat16*)feat_bf16, n, n_pts, pooled_out, h1_out, h2_out, (cudaStream_t)stream);
+    if (feat_dtype == ZS_BF16_SPLIT)
+        return zs_score_tc3(ctx, weight_slot, feat, n, n_pts, pooled_out, h1_out, h2_out, (cudaStream_t)stream);
+    return launch_tc(ctx, weight_slot, (const __nv_bfloat16*)feat, n, n_pts, pooled_out, h1_out, h2_out, (cudaStream_t)stream);
 }

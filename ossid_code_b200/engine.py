@@ -12,10 +12,28 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ZS_BF16, ZS_F32, ZS_F64, check
+from ._lib import ZS_BF16, ZS_BF16_SPLIT, ZS_F32, ZS_F64, check
 
 FEAT_DTYPES = {torch.float32: ZS_F32, torch.bfloat16: ZS_BF16}
 POSE_DTYPES = {torch.float32: ZS_F32, torch.float64: ZS_F64}
+
+
+def feat_code(feat: torch.Tensor) -> int:
+    """Feature tensors: (n,N,8) float32 / bfloat16, or (n,2,N,8) bfloat16 = split-bf16 planes (hi, lo)."""
+    if feat.ndim == 4:
+        if feat.dtype != torch.bfloat16 or feat.shape[1] != 2 or feat.shape[3] != 8:
+            raise ValueError(f"split features must be (n,2,N,8) bfloat16, got {tuple(feat.shape)} {feat.dtype}")
+        return ZS_BF16_SPLIT
+    if feat.ndim != 3 or feat.shape[2] != 8 or feat.dtype not in FEAT_DTYPES:
+        raise ValueError(f"point_x must be (n,N,8) float32/bfloat16, got {tuple(feat.shape)} {feat.dtype}")
+    return FEAT_DTYPES[feat.dtype]
+
+
+def split_bf16(x: torch.Tensor) -> torch.Tensor:
+    """(n,N,8) float32 -> (n,2,N,8) bfloat16: hi = bf16(x), lo = bf16(x - hi) (what zs_features writes for ZS_BF16_SPLIT)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.to(torch.float32)).to(torch.bfloat16)
+    return torch.stack([hi, lo], dim=1).contiguous()
 
 
 def _dev_f32(x, device) -> torch.Tensor:
@@ -217,40 +235,56 @@ class ZsContext:
 
     def features(self, slot: int, poses12, keep_idx: Optional[torch.Tensor] = None, n_keep: Optional[int] = None,
                  dtype=torch.float32, want_uv: bool = False, want_mask: bool = False, want_viol: bool = False,
-                 out: Optional[torch.Tensor] = None):
+                 out: Optional[torch.Tensor] = None, split: bool = False):
+        """``split=True`` (or a 4-D ``out``): split-bf16 features (n,2,N,8) for the fp32-accurate tensor-core scorer."""
         N = self.obj_npts[slot]
         if keep_idx is not None:
             n_keep = keep_idx.shape[0]
         elif n_keep is None:
             n_keep = poses12.shape[0]
-        feat = out if out is not None else torch.empty((n_keep, N, 8), dtype=dtype, device=self.device)
+        if out is not None:
+            feat = out
+        elif split:
+            feat = torch.empty((n_keep, 2, N, 8), dtype=torch.bfloat16, device=self.device)
+        else:
+            feat = torch.empty((n_keep, N, 8), dtype=dtype, device=self.device)
         uv = torch.empty((n_keep, N, 2), dtype=torch.int32, device=self.device) if want_uv else None
         mask = torch.empty((n_keep, N), dtype=torch.uint8, device=self.device) if want_mask else None
         viol = torch.empty((n_keep,), dtype=torch.int32, device=self.device) if want_viol else None
         self._ck(self.lib.zs_features(self.h, slot, poses12.data_ptr(),
                                       keep_idx.data_ptr() if keep_idx is not None else None, n_keep,
-                                      feat.data_ptr(), FEAT_DTYPES[feat.dtype],
+                                      feat.data_ptr(), feat_code(feat),
                                       uv.data_ptr() if want_uv else None, mask.data_ptr() if want_mask else None,
                                       viol.data_ptr() if want_viol else None, self._stream()), "zs_features")
         return feat, uv, mask, viol
 
     def score(self, wslot: int, feat: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """feat (n,N,8) float32 -> fp32 CUDA-core path; bfloat16 -> tcgen05 path."""
-        if feat.ndim != 3 or feat.shape[2] != 8 or feat.dtype not in FEAT_DTYPES:
-            raise ValueError(f"point_x must be (n,N,8) float32/bfloat16, got {tuple(feat.shape)} {feat.dtype}")
+        """feat (n,N,8) bfloat16 -> bf16 tcgen05 path (1e-2); (n,2,N,8) split-bf16 -> fp32-accurate tcgen05 path;
+        (n,N,8) float32 -> fp32 CUDA-core path (both 1e-4)."""
+        code = feat_code(feat)
         feat = feat.contiguous()
-        n, N = feat.shape[0], feat.shape[1]
+        n, N = feat.shape[0], feat.shape[-2]
         scores = out if out is not None else torch.empty((n,), dtype=torch.float32, device=self.device)
-        code = FEAT_DTYPES[feat.dtype]
-        self._ck(self.lib.zs_score(self.h, wslot, feat.data_ptr(), code, n, N, code, scores.data_ptr(),
-                                   self._stream()), "zs_score")
+        self._ck(self.lib.zs_score(self.h, wslot, feat.data_ptr(), code, n, N, ZS_BF16 if code == ZS_BF16 else ZS_F32,
+                                   scores.data_ptr(), self._stream()), "zs_score")
         return scores
 
-    def pool(self, wslot: int, feat: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Shared per-point MLP + max over points: (n,N,8) -> (n,1024) float32."""
+    def split_features(self, feat: torch.Tensor) -> torch.Tensor:
+        """(n,N,8) float32 CUDA features -> split-bf16 planes (n,2,N,8), one kernel (``zs_split_features``)."""
+        if feat.ndim != 3 or feat.shape[2] != 8 or feat.dtype != torch.float32:
+            raise ValueError(f"expected (n,N,8) float32 features, got {tuple(feat.shape)} {feat.dtype}")
+        feat = feat.contiguous()
         n, N = feat.shape[0], feat.shape[1]
+        out = torch.empty((n, 2, N, 8), dtype=torch.bfloat16, device=self.device)
+        self._ck(self.lib.zs_split_features(self.h, feat.data_ptr() if n else None, n, N, out.data_ptr() if n else None,
+                                            self._stream()), "zs_split_features")
+        return out
+
+    def pool(self, wslot: int, feat: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Shared per-point MLP + max over points: (n,N,8) or split (n,2,N,8) -> (n,1024) float32."""
+        n, N = feat.shape[0], feat.shape[-2]
         pooled = out if out is not None else torch.empty((n, 1024), dtype=torch.float32, device=self.device)
-        self._ck(self.lib.zs_pool(self.h, wslot, feat.data_ptr(), FEAT_DTYPES[feat.dtype], n, N, pooled.data_ptr(),
+        self._ck(self.lib.zs_pool(self.h, wslot, feat.data_ptr(), feat_code(feat), n, N, pooled.data_ptr(),
                                   self._stream()), "zs_pool")
         return pooled
 
@@ -263,12 +297,12 @@ class ZsContext:
         return scores
 
     def pool_debug(self, wslot: int, feat: torch.Tensor):
-        """Tensor-core pool plus the bf16-rounded layer-1 / layer-2 activations (diagnostic)."""
-        n, N = feat.shape[0], feat.shape[1]
+        """Tensor-core pool plus the layer-1 / layer-2 activations as the next layer reads them (diagnostic)."""
+        n, N = feat.shape[0], feat.shape[-2]
         pooled = torch.zeros((n, 1024), dtype=torch.float32, device=self.device)
         h1 = torch.zeros((n * N, 64), dtype=torch.float32, device=self.device)
         h2 = torch.zeros((n * N, 128), dtype=torch.float32, device=self.device)
-        self._ck(self.lib.zs_pool_debug(self.h, wslot, feat.data_ptr(), n, N, pooled.data_ptr(), h1.data_ptr(),
+        self._ck(self.lib.zs_pool_debug(self.h, wslot, feat.data_ptr(), feat_code(feat), n, N, pooled.data_ptr(), h1.data_ptr(),
                                         h2.data_ptr(), self._stream()), "zs_pool_debug")
         return pooled, h1.view(n, N, 64), h2.view(n, N, 128)
 
@@ -354,7 +388,8 @@ class ZsContext:
                                           out.data_ptr(), self._stream()), "zs_gather_poses")
         return out
 
-    # fp32-accurate scoring of a handful of hypotheses (the re-rank of the top-k candidates)
+    # fp32-accurate scoring of a handful of hypotheses (the re-rank of the top-k candidates): split-bf16 features
+    # (n,2,N,8) and the 3-term tcgen05 scorer
     def features_f32a(self, slot: int, poses12: torch.Tensor, out: torch.Tensor):
         return self.features(slot, poses12, out=out)[0]
 

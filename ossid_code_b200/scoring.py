@@ -178,7 +178,8 @@ class FrameScorer:
         if device is None:
             device = torch.cuda.current_device()
         self.ctx = ctx or get_context(device)
-        self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.precision = precision
+        self.split = precision == "fp32"      # fp32-accurate: split-bf16 features + the 3-term tcgen05 scorer + the fp32 head
         self.th, self.k, self.chunk, self.group = float(inconst_ratio_th), int(k), int(chunk), group
         self.rerank = (precision == "bf16") if rerank is None else bool(rerank and precision == "bf16")
         self._weights = list(weights)
@@ -405,14 +406,14 @@ class FrameScorer:
         ctx, k = self.ctx, self.k
         res, plan = self._resident, self._plan
         n_obj, nk = plan.n_obj, plan.n_obj * k
-        tensor_cores = self.dtype == torch.bfloat16
+        head_tc = not self.split              # tf32 tensor-core head on the bf16 path, fp32 CUDA-core head on the 1e-4 path
         self._sync_weights()
         rec = plan.rec
         S_loc, I_loc = rec[:nk].view(torch.float32).view(n_obj, k), rec[nk:2 * nk].view(n_obj, k)
         info = rec[2 * nk: 2 * nk + 2 * n_obj]
-        # 1. free-space pre-filter per object.  Tensor-core path: the kept count stays on the device (the feature and
-        #    MLP kernels read it, zs_set_dynamic_count) and buffers are laid out by capacity, so a filtered frame is as
-        #    asynchronous as an unfiltered one.  fp32 parity path: reads back one count per object.
+        # 1. free-space pre-filter per object: the kept count stays on the device (the feature and MLP kernels read it,
+        #    zs_set_dynamic_count) and buffers are laid out by capacity, so a filtered frame is as asynchronous as an
+        #    unfiltered one.
         keeps, n_keeps, n_devs = [], [], []
         filtered = self.th < 100
         for o, r in enumerate(res):
@@ -424,8 +425,6 @@ class FrameScorer:
                 keep, n_dev = ctx.filter_async(viol, ctx.obj_npts[r["slot"]], self.th, info=info[2 * o: 2 * o + 2],
                                                keep_out=plan.index_map[a: a + M],
                                                n_keep_out=plan.seg_dyn.view(-1)[4 * o + 1: 4 * o + 2])
-                if not tensor_cores:
-                    keep, n_dev = keep[: int(n_dev.item())].clone(), None
             keeps.append(keep)
             n_devs.append(n_dev)
             n_keeps.append(M if (keep is None or n_dev is not None) else keep.shape[0])     # capacity when the count is on the device
@@ -488,7 +487,7 @@ class FrameScorer:
             hi = offs[members[-1]] + n_keeps[members[-1]]
             if hi > lo:
                 t = self._mark("head", hi - lo)
-                ctx.head(ws, self._pooled[lo:hi], tensor_cores, out=self._scores[lo:hi])
+                ctx.head(ws, self._pooled[lo:hi], head_tc, out=self._scores[lo:hi])
                 self._mark(None, 0, t)
         # 5. per-object top-k in one launch (one CTA per object), written straight into this rank's candidate record;
         #    indices mapped back to global hypothesis indices inside the kernel.  Without a pre-filter the segment table
@@ -496,13 +495,8 @@ class FrameScorer:
         t = self._mark("topk", n_obj)
         if all(kp is None for kp in keeps):
             ctx.topk_segments(self._scores, plan.seg, k, out=(S_loc, I_loc))
-        elif all(d is not None or n_keeps[o] == 0 for o, d in enumerate(n_devs)):
-            ctx.topk_segments(self._scores, plan.seg_dyn, k, index_map=plan.index_map, out=(S_loc, I_loc))
         else:
-            for o, r in enumerate(res):
-                ts, ti = ctx.topk(self._scores[offs[o]: offs[o] + n_keeps[o]], k, r["lo"], index_map=keeps[o])
-                S_loc[o].copy_(ts)
-                I_loc[o].copy_(ti)
+            ctx.topk_segments(self._scores, plan.seg_dyn, k, index_map=plan.index_map, out=(S_loc, I_loc))
         if self.rerank:          # the candidates' poses travel with the record: any rank can re-score any candidate
             ctx.gather_poses(self._p12[self._buf], I_loc, plan.pose_seg, out=rec[plan.pose_at:].view(torch.float32))
         self._mark(None, 0, t)
@@ -536,10 +530,12 @@ class FrameScorer:
         return S, I, plan.P
 
     def _feat_buf(self, rows: int, N: int, rows_cap: int):
-        need = rows * N * 8
-        if self._feat is None or self._feat.numel() < need or self._feat.dtype != self.dtype:
-            self._feat = torch.empty((max(need, rows_cap * N * 8),), dtype=self.dtype, device=self.ctx.device)
-        return self._feat[:need].view(rows, N, 8)
+        """Feature rows of a chunk: (rows,N,8) bf16, or split-bf16 planes (rows,2,N,8) on the fp32-accurate path."""
+        per = N * 8 * (2 if self.split else 1)
+        need = rows * per
+        if self._feat is None or self._feat.numel() < need:
+            self._feat = torch.empty((max(need, rows_cap * per),), dtype=torch.bfloat16, device=self.ctx.device)
+        return self._feat[:need].view(rows, 2, N, 8) if self.split else self._feat[:need].view(rows, N, 8)
 
     def _rerank(self, S, I, P):
         """Re-score the k candidates of every object with the fp32-accurate scorer and order them by that score
@@ -552,7 +548,7 @@ class FrameScorer:
         if rr is None or rr["rows"] < n_obj * k or rr["N"] < Nmax:
             rows = n_obj * k
             rr = self._rr = dict(rows=rows, N=Nmax,
-                                 feat=torch.zeros((rows * Nmax * 8,), dtype=torch.float32, device=ctx.device),
+                                 feat=torch.zeros((rows * Nmax * 16,), dtype=torch.bfloat16, device=ctx.device),
                                  pooled=torch.zeros((rows, 1024), dtype=torch.float32, device=ctx.device),
                                  scores=torch.zeros((rows,), dtype=torch.float32, device=ctx.device),
                                  out=torch.zeros((2 * rows,), dtype=torch.int32, device=ctx.device))
@@ -564,14 +560,14 @@ class FrameScorer:
             r0 = plan.rr_row[members[0]] * k
             if same_n:
                 N = Nmax
-                feat = rr["feat"][: n_obj * k * N * 8].view(n_obj * k, N, 8)
+                feat = rr["feat"][: n_obj * k * N * 16].view(n_obj * k, 2, N, 8)
                 for o in members:
                     ctx.features_f32a(o, P[o], out=feat[plan.rr_row[o] * k: plan.rr_row[o] * k + k])
                 ctx.pool_f32a(ws, feat[r0: r0 + len(members) * k], out=rr["pooled"][r0: r0 + len(members) * k])
             else:
                 for o in members:
                     N = ctx.obj_npts[o]
-                    feat = rr["feat"][: k * N * 8].view(k, N, 8)
+                    feat = rr["feat"][: k * N * 16].view(k, 2, N, 8)
                     ctx.features_f32a(o, P[o], out=feat)
                     row = plan.rr_row[o] * k
                     ctx.pool_f32a(ws, feat, out=rr["pooled"][row: row + k])
@@ -603,7 +599,7 @@ class FrameScorer:
             if not idx:
                 continue
             p12 = poses_to_rt12(torch.as_tensor(np.asarray(ob["pose_hypos"])[idx]), ctx.device)
-            _, uv, _, _ = ctx.features(r["slot"], p12, dtype=self.dtype, want_uv=True)
+            _, uv, _, _ = ctx.features(r["slot"], p12, dtype=torch.float32, want_uv=True)
             out, st = ctx.icp_refine(p12, ob["_zs_host"][0], uv, max_dist=icp_max_dist, max_iter=max_iter)
             pending.append((o, len(idx), out, st))
         for o, m, out, st in pending:                       # read back after every object's launches are queued

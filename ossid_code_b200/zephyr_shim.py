@@ -85,8 +85,8 @@ class ScoreDataset:
     """``ScoreDataset(datapoints, dataset_root, dataset_name, args, mode='test')`` -- featuriser only.
 
     Honoured ``args`` fields: ``inconst_ratio_th`` (online_learning.py:195), plus two of this
-    build: ``zs_precision`` ("fp32" -> float32 features + CUDA-core scorer, "bf16" (default) ->
-    bfloat16 features + tcgen05 scorer) and ``zs_device``.
+    build: ``zs_precision`` ("fp32" -> float32 features, scored to 1e-4 by the 3-term bf16-split tcgen05 scorer;
+    "bf16" (default) -> bfloat16 features + bf16 tcgen05 scorer, 1e-2) and ``zs_device``.
     """
 
     dim_point = W.DIM_POINT
@@ -151,6 +151,9 @@ class PointNet2SSG(torch.nn.Module):
         _next_weight_slot[0] += 1
         self._uploaded = None
         self._token = object()
+        # float32 point_x: scored by the 3-term bf16-split tcgen05 kernel (1e-4); zs_fp32_kernel="cuda" selects the
+        # CUDA-core fp32 kernel that implements the same arithmetic without tensor cores
+        self.fp32_on_cuda_cores = getattr(args, "zs_fp32_kernel", "tensor") == "cuda"
         self.eval()
 
     @property
@@ -179,6 +182,8 @@ class PointNet2SSG(torch.nn.Module):
             raise RuntimeError("point_x must be a CUDA tensor: there is no CPU scoring path")
         ctx = get_context(x.device)
         self._sync_weights(ctx)
+        if x.dtype == torch.float32 and x.ndim == 3 and not self.fp32_on_cuda_cores:
+            x = ctx.split_features(x)          # fp32-accurate path on the tensor cores (3-term bf16 split)
         return ctx.score(self._slot, x).reshape(-1, 1)
 
 

@@ -371,6 +371,72 @@ def test_tc_scorer_layers_match_bf16_oracle(ctx, n, N):
     assert float((scores - ref32).abs().max()) <= SCORE_BF16_RTOL * float(ref32.abs().max()) + 1e-6
 
 
+def _oracle_layers_f32(x, w):
+    h1 = torch.relu(x @ w["W1"].T + w["b1"])
+    h2 = torch.relu(h1 @ w["W2"].T + w["b2"])
+    h3 = torch.relu(h2 @ w["W3"].T + w["b3"])
+    return h1, h2, h3.max(dim=1).values
+
+
+@pytest.mark.parametrize("n,N", [(1, 128), (2, 256), (3, 100), (5, 1000), (150, 130), (1, 1), (40, 1000),
+                                 (7, 300), (3, 4000), (149, 257), (2, 127), (5, 384), (17, 1000), (19, 1000), (73, 1000)])
+def test_tc3_split_scorer_matches_fp32_oracle(ctx, n, N):
+    """fp32-accurate tcgen05 path (every product as bf16 hi.hi + lo.hi + hi.lo, fp32 accumulate): layer by layer and end
+    scores vs the fp32 oracle at 1e-4, on the shapes of the bf16 test plus hypothesis counts around the 18 pair-groups."""
+    from ossid_code_b200.engine import split_bf16
+    g = torch.Generator().manual_seed(11 * n + N)
+    x = torch.randn(n, N, 8, generator=g) * 0.5
+    w = weights.seeded_folded(2)
+    ctx.set_weights(1, w)
+    xs = split_bf16(x).to(ctx.device)
+    assert torch.equal(ctx.split_features(x.to(ctx.device)), xs), "zs_split_features != hi/lo split on the host"
+    pooled, h1, h2 = ctx.pool_debug(1, xs)
+    r1, r2, rp = _oracle_layers_f32(x, w)
+    e1 = float((h1.cpu() - r1).abs().max()) / float(r1.abs().max())
+    e2 = float((h2.cpu() - r2).abs().max()) / float(r2.abs().max())
+    ep = float((pooled.cpu() - rp).abs().max()) / float(rp.abs().max())
+    print(f"n={n} N={N}: rel err h1 {e1:.2e} h2 {e2:.2e} pooled {ep:.2e}")
+    assert e1 <= 5e-5, "layer 1 differs"
+    assert e2 <= 5e-5, "layer 2 differs"
+    assert ep <= 5e-5, "layer 3 + max-pool differs"
+    assert torch.equal(ctx.pool(1, xs), pooled), "the debug build of the launch changes the result"
+    scores = ctx.score(1, xs).cpu()
+    ref = zo.scorer(x, w)
+    assert float((scores - ref).abs().max()) <= SCORE_F32_RTOL * float(ref.abs().max()) + 1e-6
+    cuda_core = ctx.score(1, x.to(ctx.device)).cpu()                       # the CUDA-core fp32 kernel agrees as well
+    assert float((scores - cuda_core).abs().max()) <= SCORE_F32_RTOL * float(ref.abs().max()) + 1e-6
+
+
+def test_tc3_split_scorer_batch_position_invariance(ctx):
+    from ossid_code_b200.engine import split_bf16
+    g = torch.Generator().manual_seed(5)
+    x = split_bf16(torch.randn(100, 1000, 8, generator=g) * 0.5).to(ctx.device)
+    ctx.set_weights(1, weights.seeded_folded(2))
+    s = ctx.score(1, x)
+    perm = torch.randperm(100, generator=g).to(ctx.device)
+    assert torch.equal(ctx.score(1, x[perm].contiguous()), s[perm]), "split tensor-core scores depend on batch position"
+    assert torch.equal(ctx.score(1, x[:7].contiguous()), s[:7])
+
+
+def test_split_features_are_the_split_of_the_fp32_features(ctx):
+    """zs_features with ZS_BF16_SPLIT == hi/lo split of the float32 features of the same (hot) kernel, bit for bit."""
+    from ossid_code_b200.engine import split_bf16
+    for intr, n_pts, n_hypo in (("lmo", 1000, 300), ("tiny", 77, 50), ("hd", 4000, 20)):
+        sc = syn.make_scene(43, intr, n_obj=1, n_pts=n_pts, n_hypo=n_hypo)
+        ob = sc["objects"][0]
+        ctx.set_frame_u8(sc["img"], sc["depth"], glue.K2meta(sc["cam_K"]))
+        ctx.set_object(0, ob["model_points"], ob["model_colors"], ob["model_normals"])
+        p12 = poses_to_rt12(ob["pose_hypos"], ctx.device)
+        f32, _, _, _ = ctx.features(0, p12, dtype=torch.float32)
+        sp, _, _, _ = ctx.features(0, p12, split=True)
+        assert sp.shape == (n_hypo, 2, n_pts, 8) and torch.equal(sp, split_bf16(f32))
+        recon = sp[:, 0].float() + sp[:, 1].float()
+        assert float((recon - f32).abs().max()) <= 2 ** -16 * float(f32.abs().max())
+        keep = torch.arange(0, n_hypo, 3, dtype=torch.int32, device=ctx.device)
+        spk, _, _, _ = ctx.features(0, p12, keep_idx=keep, split=True)
+        assert torch.equal(spk, sp[keep.long()])
+
+
 def test_tc_scorer_batch_position_invariance(ctx):
     g = torch.Generator().manual_seed(3)
     x = (torch.randn(300, 1000, 8, generator=g) * 0.5).to(torch.bfloat16).to(ctx.device)

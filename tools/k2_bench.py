@@ -1,23 +1,28 @@
-"""Micro-benchmark of the tensor-core MLP kernel alone (zs_pool on random bf16 features)."""
-import os, sys, torch
+"""Throughput of the two tensor-core MLP kernels alone (CUDA events): python tools/k2_bench.py [n] [N] [reps].
+bf16: zs_k_mlp_tc on (n,N,8) bf16 features; split: zs_k_mlp_tc3 (fp32-accurate, 3-term) on (n,2,N,8) planes."""
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
 from ossid_code_b200 import weights
-from ossid_code_b200.engine import get_context
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+from ossid_code_b200.engine import get_context, split_bf16
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-iters = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 ctx = get_context(0)
 ctx.set_weights(0, weights.seeded_folded(0))
-x = (torch.randn(n, N, 8, device=ctx.device) * 0.5).to(torch.bfloat16)
-pooled = torch.empty(n, 1024, device=ctx.device)
-for _ in range(3): ctx.pool(0, x, out=pooled)
-torch.cuda.synchronize()
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-for _ in range(iters): ctx.pool(0, x, out=pooled)
-b.record(); torch.cuda.synchronize()
-ms = a.elapsed_time(b) / iters
-fl = 2.0 * n * N * (8 * 64 + 64 * 128 + 128 * 1024)
-tiles = n / 74 * -(-N // 128)
-print(f"iters={iters} exp={os.environ.get('ZS_TC_EXPERIMENT','0')} n={n} N={N}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s (algorithmic)  "
-      f"{ms*1e-3*1.965e9/tiles:.0f} cycles/tile @1965MHz  {n/ms/1e3:.2f} M hyp/s")
+x = torch.randn(n, N, 8, generator=torch.Generator().manual_seed(0)) * 0.5
+flops = 2.0 * (8 * 64 + 64 * 128 + 128 * 1024) * n * N
+for name, feat in (("bf16", x.to(torch.bfloat16).to(ctx.device)), ("split", split_bf16(x).to(ctx.device))):
+    out = torch.empty((n, 1024), dtype=torch.float32, device=ctx.device)
+    for _ in range(2):
+        ctx.pool(0, feat, out=out)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        ctx.pool(0, feat, out=out)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    print(f"{name}: n={n} N={N}: {ms:.3f} ms/launch, {flops / ms / 1e9:.1f} TFLOP/s algorithmic, {n / ms / 1e3:.3f} M hyp/s")
