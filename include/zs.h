@@ -153,6 +153,14 @@ ZS_API int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const int3
                 void* feat_out, int feat_dtype, int32_t* uv_out, uint8_t* mask_out,
                 int32_t* viol_out, void* stream);
 
+/* zs_features (no side outputs) for several objects of the frame in ONE launch: segment i featurises hypotheses
+ * keep_idx[i][0..n_keep[i]) (keep_idx NULL or keep_idx[i] NULL = 0..n_keep[i]) of poses[i] against the cloud in
+ * obj_slots[i] and writes feat_out[i].  All array arguments are [host] arrays of n_seg entries holding [dev] pointers;
+ * n_dev / n_off (nullable) are the per-segment device-side counts of zs_set_dynamic_count (which this call ignores). */
+ZS_API int zs_features_multi(zs_ctx* ctx, int n_seg, const int32_t* obj_slots, const float* const* poses,
+                      const int32_t* const* keep_idx, const int32_t* n_keep, const int32_t* const* n_dev,
+                      const int32_t* n_off, void* const* feat_out, int feat_dtype, void* stream);
+
 /* Scorer forward, `model({"point_x": point_x})` (zephyr_utils.py:34).  feat [dev] [n][n_pts][8] in feat_dtype
  * ([n][2][n_pts][8] bf16 for ZS_BF16_SPLIT).  precision ZS_BF16 (feat ZS_BF16): bf16 tcgen05 path, 1e-2;
  * precision ZS_F32: fp32-accurate, 1e-4 -- feat ZS_BF16_SPLIT: tcgen05 with 3-term bf16-split products and the fp32

@@ -35,6 +35,7 @@ SIGNATURES = {
     "zs_merge_topk": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "zs_gather_poses": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "zs_features": (_i, [_p, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
+    "zs_features_multi": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
     "zs_score": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p]),
     "zs_split_features": (_i, [_p, _p, _i, _i, _p, _p]),
     "zs_pool": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),

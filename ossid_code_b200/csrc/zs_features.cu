@@ -225,26 +225,19 @@ __device__ __forceinline__ void st_f32_row(float* p, float4 lo, float4 hi, bool 
 
 // kFmt: ZS_F32 (32-byte rows), ZS_BF16 (16-byte rows) or ZS_BF16_SPLIT (per hypothesis a plane of bf16(x) rows followed by
 // a plane of bf16(x - bf16(x)) rows: the two K halves of the fp32-accurate scorer's layer-1 operand, zs_score_tc3.cu).
+// The units of ONE object that this warp owns: first_unit, first_unit + n_warps, ...
 template <int kFmt, bool kSmem>
-__global__ void __launch_bounds__(kMaxThreads, 1)
-zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
-                  const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out, int aligned32,
-                  const int32_t* __restrict__ n_dev, int n_off) {
-    n_keep = zs_dyn_count(n_dev, n_off, n_keep);
-    extern __shared__ __align__(16) char smem[];
-    float4 *sA, *sB;
-    float* sV;
-    stage_cloud<kSmem>(o, sA, sB, sV, smem);
+__device__ __forceinline__ void hot_units(const obj_view& o, const zs_cam& cam, const float4* __restrict__ frame,
+                                          const float* __restrict__ poses, const int32_t* __restrict__ keep_idx, int n_keep,
+                                          void* __restrict__ feat_out, int aligned32, const float4* sA, const float4* sB,
+                                          const float* sV, long long first_unit, int n_warps) {
     constexpr int kIlp = 2, kChunk = 256;
     const int lane = threadIdx.x & 31;
-    const int warps_per_cta = blockDim.x >> 5;
-    const int warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
-    const int n_warps = gridDim.x * warps_per_cta;
     const int N = o.n_pts;
     const float fW = (float)cam.W, fH = (float)cam.H;
     const int n_chunks = (N + kChunk - 1) / kChunk;
     const long long n_units = (long long)n_keep * n_chunks;
-    for (long long u = warp; u < n_units; u += n_warps) {
+    for (long long u = first_unit; u < n_units; u += n_warps) {
         const int hk = (int)(u / n_chunks);
         const int p_begin = (int)(u - (long long)hk * n_chunks) * kChunk;
         const int p_end = min(N, p_begin + kChunk);
@@ -311,6 +304,58 @@ zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, cons
                 }
             }
         }
+    }
+}
+
+template <int kFmt, bool kSmem>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
+                  const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out, int aligned32,
+                  const int32_t* __restrict__ n_dev, int n_off) {
+    n_keep = zs_dyn_count(n_dev, n_off, n_keep);
+    extern __shared__ __align__(16) char smem[];
+    float4 *sA, *sB;
+    float* sV;
+    stage_cloud<kSmem>(o, sA, sB, sV, smem);
+    const int warps_per_cta = blockDim.x >> 5;
+    hot_units<kFmt, kSmem>(o, cam, frame, poses, keep_idx, n_keep, feat_out, aligned32, sA, sB, sV,
+                           blockIdx.x * warps_per_cta + (threadIdx.x >> 5), gridDim.x * warps_per_cta);
+}
+
+// Several objects in one launch (a frame's objects share the frame but not the model cloud): every CTA walks the
+// segment list, re-stages the cloud of each segment it has units of, and takes its grid-stride share of that
+// segment's units; the first unit of segment s goes to CTA s * (grid / segments), so that many short segments (the
+// re-rank: k candidates per object) run side by side instead of all starting on CTA 0.
+struct feat_seg {
+    obj_view o;
+    const float* poses;
+    const int32_t* keep_idx;
+    const int32_t* n_dev;
+    void* out;
+    int n_keep, n_off, aligned32, pad_;
+};
+constexpr int kMaxSegsPerLaunch = 32;
+struct feat_segs { feat_seg s[kMaxSegsPerLaunch]; };
+
+template <int kFmt, bool kSmem>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+zs_k_features_multi(const __grid_constant__ feat_segs segs, int n_seg, zs_cam cam, const float4* __restrict__ frame) {
+    extern __shared__ __align__(16) char smem[];
+    const int warps_per_cta = blockDim.x >> 5;
+    const int n_warps = gridDim.x * warps_per_cta;
+    const int stride_ctas = max(1, (int)gridDim.x / n_seg);
+    for (int sgi = 0; sgi < n_seg; ++sgi) {
+        const feat_seg& sg = segs.s[sgi];
+        const int n_keep = zs_dyn_count(sg.n_dev, sg.n_off, sg.n_keep);
+        const long long n_units = (long long)n_keep * ((sg.o.n_pts + 255) / 256);
+        const int cta_first = (int)(((long long)blockIdx.x + gridDim.x - (long long)(sgi * stride_ctas) % gridDim.x) % gridDim.x);
+        if ((long long)cta_first * warps_per_cta >= n_units) continue;            // CTA-uniform: nothing of this segment here
+        float4 *sA, *sB;
+        float* sV;
+        __syncthreads();                                                           // previous segment's cloud no longer in use
+        stage_cloud<kSmem>(sg.o, sA, sB, sV, smem);
+        hot_units<kFmt, kSmem>(sg.o, cam, frame, sg.poses, sg.keep_idx, n_keep, sg.out, sg.aligned32, sA, sB, sV,
+                               (long long)cta_first * warps_per_cta + (threadIdx.x >> 5), n_warps);
     }
 }
 
@@ -556,6 +601,64 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
     else                       { if (in_smem) ZS_LAUNCH_FEAT(ZS_F32, true); else ZS_LAUNCH_FEAT(ZS_F32, false); }
 #undef ZS_LAUNCH_FEAT
     ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
+extern "C" int zs_features_multi(zs_ctx* ctx, int n_seg, const int32_t* obj_slots, const float* const* poses,
+                                 const int32_t* const* keep_idx, const int32_t* n_keep, const int32_t* const* n_dev,
+                                 const int32_t* n_off, void* const* feat_out, int feat_dtype, void* stream) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (n_seg == 0) return ZS_OK;
+    if (n_seg < 0 || !obj_slots || !poses || !n_keep || !feat_out ||
+        (feat_dtype != ZS_F32 && feat_dtype != ZS_BF16 && feat_dtype != ZS_BF16_SPLIT))
+        return zs_fail(ctx, ZS_ERR_INVALID, "zs_features_multi arguments");
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int s0 = 0; s0 < n_seg; s0 += kMaxSegsPerLaunch) {
+        feat_segs segs;
+        zs_cam cam;
+        int m = 0, max_pts = 0;
+        long long units = 0;
+        for (int i = s0; i < n_seg && m < kMaxSegsPerLaunch; ++i) {
+            if (n_keep[i] == 0) continue;
+            obj_view o;
+            int rc = check_obj(ctx, obj_slots[i], poses[i], o, cam);
+            if (rc) return rc;
+            if (n_keep[i] < 0 || !feat_out[i] || ((uintptr_t)feat_out[i] & 15))
+                return zs_fail(ctx, ZS_ERR_INVALID, "segment %d: n_keep %d / feat_out alignment", i, n_keep[i]);
+            feat_seg& g = segs.s[m++];
+            g.o = o;
+            g.poses = poses[i];
+            g.keep_idx = keep_idx ? keep_idx[i] : nullptr;
+            g.n_dev = n_dev ? n_dev[i] : nullptr;
+            g.n_off = (n_dev && n_off) ? n_off[i] : 0;
+            g.out = feat_out[i];
+            g.n_keep = n_keep[i];
+            g.aligned32 = (((uintptr_t)feat_out[i] & 31) == 0);
+            g.pad_ = 0;
+            max_pts = o.n_pts > max_pts ? o.n_pts : max_pts;
+            units += (long long)n_keep[i] * ((o.n_pts + 255) / 256);
+        }
+        if (m == 0) continue;
+        const bool in_smem = cloud_smem(max_pts) <= kCloudSmemMax;
+        const cta_shape cs = shape_for(in_smem ? cloud_smem(max_pts) : 0, 0);
+        // enough CTAs for every segment to start on its own one; a big launch fills the machine
+        int grid = grid_for(ctx, units, cs.ctas_per_sm, cs.threads / 32);
+        if (grid < m) grid = m < ctx->sm_count ? m : ctx->sm_count;
+        const float4* frame = ctx->frame.packed;
+        int rc;
+#define ZS_LAUNCH_MULTI(FMT, SM)                                                                        \
+    do {                                                                                                \
+        rc = opt_in_smem(ctx, zs_k_features_multi<FMT, SM>, cs.smem);                                   \
+        if (rc) return rc;                                                                              \
+        zs_k_features_multi<FMT, SM><<<grid, cs.threads, cs.smem, st>>>(segs, m, cam, frame);           \
+    } while (0)
+        if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_MULTI(ZS_BF16, true); else ZS_LAUNCH_MULTI(ZS_BF16, false); }
+        else if (feat_dtype == ZS_BF16_SPLIT) { if (in_smem) ZS_LAUNCH_MULTI(ZS_BF16_SPLIT, true); else ZS_LAUNCH_MULTI(ZS_BF16_SPLIT, false); }
+        else { if (in_smem) ZS_LAUNCH_MULTI(ZS_F32, true); else ZS_LAUNCH_MULTI(ZS_F32, false); }
+#undef ZS_LAUNCH_MULTI
+        ZS_LAUNCHED(ctx);
+    }
     return ZS_OK;
 }
 

@@ -163,6 +163,49 @@ zs_k_fc(const float* __restrict__ in, const float* __restrict__ Wt, const float*
     }
 }
 
+// The same for a handful of rows (the fp32 re-rank of the top-k candidates: n = k x objects, a few hundred): a
+// 128-row tile would leave all but a few SMs idle, so a CTA takes 8 rows x 64 output channels and its four warp pairs
+// split K (partial sums reduced through shared memory).  grid (ceil(n/8), CO/64), 256 threads.
+constexpr int kSmallRows = 8, kSmallCo = 64;
+template <bool kRelu>
+__global__ void __launch_bounds__(256)
+zs_k_fc_small(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ b,
+              float* __restrict__ out, int n, int K, int CO) {
+    extern __shared__ __align__(16) float sm_small[];
+    float* in_t = sm_small;                                  // [K][8 rows]
+    float* part = sm_small + (size_t)K * kSmallRows;         // [4 k-slices][8 rows][64 channels]
+    const int tid = threadIdx.x, c = tid & 63, ks = tid >> 6;
+    const int r0 = blockIdx.x * kSmallRows, co = blockIdx.y * kSmallCo + c;
+    for (int i = tid; i < kSmallRows * K; i += 256) {
+        const int r = i / K, k = i - r * K;
+        in_t[k * kSmallRows + r] = (r0 + r < n) ? __ldg(in + (size_t)(r0 + r) * K + k) : 0.f;
+    }
+    __syncthreads();
+    float acc[kSmallRows];
+#pragma unroll
+    for (int r = 0; r < kSmallRows; ++r) acc[r] = 0.f;
+    const int kq = K / 4;
+#pragma unroll 4
+    for (int k = ks * kq; k < (ks + 1) * kq; ++k) {
+        const float w = __ldg(Wt + (size_t)k * CO + co);
+        const float4 a0 = *reinterpret_cast<const float4*>(in_t + k * kSmallRows);
+        const float4 a1 = *reinterpret_cast<const float4*>(in_t + k * kSmallRows + 4);
+        acc[0] = fmaf(w, a0.x, acc[0]); acc[1] = fmaf(w, a0.y, acc[1]); acc[2] = fmaf(w, a0.z, acc[2]); acc[3] = fmaf(w, a0.w, acc[3]);
+        acc[4] = fmaf(w, a1.x, acc[4]); acc[5] = fmaf(w, a1.y, acc[5]); acc[6] = fmaf(w, a1.z, acc[6]); acc[7] = fmaf(w, a1.w, acc[7]);
+    }
+#pragma unroll
+    for (int r = 0; r < kSmallRows; ++r) part[(ks * kSmallRows + r) * kSmallCo + c] = acc[r];
+    __syncthreads();
+    for (int i = tid; i < kSmallRows * kSmallCo; i += 256) {
+        const int r = i >> 6, cc = i & 63;
+        float v = ((part[(0 * kSmallRows + r) * kSmallCo + cc] + part[(1 * kSmallRows + r) * kSmallCo + cc]) +
+                   (part[(2 * kSmallRows + r) * kSmallCo + cc] + part[(3 * kSmallRows + r) * kSmallCo + cc])) +
+                  __ldg(b + blockIdx.y * kSmallCo + cc);
+        if (kRelu) v = fmaxf(v, 0.f);
+        if (r0 + r < n) out[(size_t)(r0 + r) * CO + blockIdx.y * kSmallCo + cc] = v;
+    }
+}
+
 // scores[h] = g2[h] . F3 + c3 ; one warp per hypothesis.
 __global__ void zs_k_fc_out(const float* __restrict__ g2, const float* __restrict__ F3, const float* __restrict__ c3,
                             float* __restrict__ scores, int n) {
@@ -215,6 +258,18 @@ static int head_impl(zs_ctx* ctx, int slot, const float* pooled, int n, float* s
                      int precision, cudaStream_t st) {
     if (precision == ZS_BF16) return zs_head_tc(ctx, slot, pooled, n, scores, g1, st);   // tensor cores (tf32)
     const zs_weights& w = ctx->w[slot];
+    if (n <= 1024) {         // a handful of rows (the re-rank): small tiles so that the whole GPU takes part
+        const int tiles = (n + kSmallRows - 1) / kSmallRows;
+        const size_t sm1 = (size_t)(1024 * kSmallRows + 4 * kSmallRows * kSmallCo) * sizeof(float);
+        const size_t sm2 = (size_t)(512 * kSmallRows + 4 * kSmallRows * kSmallCo) * sizeof(float);
+        zs_k_fc_small<true><<<dim3(tiles, 512 / kSmallCo), 256, sm1, st>>>(pooled, w.f32t + kOffF1t, w.f32 + ZS_OFF_C1, g1, n, 1024, 512);
+        ZS_LAUNCHED(ctx);
+        zs_k_fc_small<true><<<dim3(tiles, 256 / kSmallCo), 256, sm2, st>>>(g1, w.f32t + kOffF2t, w.f32 + ZS_OFF_C2, g2, n, 512, 256);
+        ZS_LAUNCHED(ctx);
+        zs_k_fc_out<<<(n * 32 + 255) / 256, 256, 0, st>>>(g2, w.f32 + ZS_OFF_F3, w.f32 + ZS_OFF_C3, scores, n);
+        ZS_LAUNCHED(ctx);
+        return ZS_OK;
+    }
     dim3 g_fc1((n + kRows - 1) / kRows, 512 / 128), g_fc2((n + kRows - 1) / kRows, 256 / 128);
     zs_k_fc<true><<<g_fc1, kThreadsMlp, 0, st>>>(pooled, w.f32t + kOffF1t, w.f32 + ZS_OFF_C1, g1, n, 1024, 512);
     ZS_LAUNCHED(ctx);

@@ -269,6 +269,29 @@ class ZsContext:
                                    scores.data_ptr(), self._stream()), "zs_score")
         return scores
 
+    def features_multi(self, segments):
+        """``zs_features_multi``: featurise several objects of the frame in one launch.  ``segments``: iterable of
+        ``(slot, poses12, out)`` or ``(slot, poses12, out, keep_idx, n_dev, n_off)``; every ``out`` has the same format
+        ((n,N,8) float32 / bfloat16 or split (n,2,N,8)) and as many rows as hypotheses (its capacity with ``n_dev``)."""
+        segs = [tuple(sg) + (None,) * (6 - len(sg)) for sg in segments if sg[2].shape[0] > 0]
+        if not segs:
+            return
+        n = len(segs)
+        code = feat_code(segs[0][2])
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        slots = (C.c_int32 * n)(*[sg[0] for sg in segs])
+        poses = (C.c_void_p * n)(*[sg[1].data_ptr() for sg in segs])
+        outs = (C.c_void_p * n)(*[sg[2].data_ptr() for sg in segs])
+        counts = (C.c_int32 * n)(*[sg[2].shape[0] for sg in segs])
+        keeps = (C.c_void_p * n)(*[ptr(sg[3]) for sg in segs])
+        ndev = (C.c_void_p * n)(*[ptr(sg[4]) for sg in segs])
+        noff = (C.c_int32 * n)(*[int(sg[5] or 0) for sg in segs])
+        for sg in segs:
+            if feat_code(sg[2]) != code:
+                raise ValueError("features_multi: every segment must use the same feature format")
+        self._ck(self.lib.zs_features_multi(self.h, n, slots, poses, keeps, counts, ndev, noff, outs, code, self._stream()),
+                 "zs_features_multi")
+
     def split_features(self, feat: torch.Tensor) -> torch.Tensor:
         """(n,N,8) float32 CUDA features -> split-bf16 planes (n,2,N,8), one kernel (``zs_split_features``)."""
         if feat.ndim != 3 or feat.shape[2] != 8 or feat.dtype != torch.float32:

@@ -454,11 +454,12 @@ class FrameScorer:
                     ce = min(cs + self.chunk, hi)
                     feat = self._feat_buf(ce - cs, N, min(self.chunk, hi - lo))
                     t = self._mark("features", (ce - cs) * N)
+                    segs = []
                     for o in members:
                         a, b = max(cs, offs[o]), min(ce, offs[o] + n_keeps[o])
                         if a < b:
-                            ctx.features(res[o]["slot"], res[o]["poses12"][a - offs[o]: b - offs[o]], n_keep=b - a,
-                                         out=feat[a - cs: b - cs])
+                            segs.append((res[o]["slot"], res[o]["poses12"][a - offs[o]: b - offs[o]], feat[a - cs: b - cs]))
+                    ctx.features_multi(segs)              # the chunk's objects in one launch
                     t = self._mark("pool", (ce - cs) * N, t)
                     ctx.pool(ws, feat, out=self._pooled[cs:ce])
                     self._mark(None, 0, t)
@@ -561,8 +562,8 @@ class FrameScorer:
             if same_n:
                 N = Nmax
                 feat = rr["feat"][: n_obj * k * N * 16].view(n_obj * k, 2, N, 8)
-                for o in members:
-                    ctx.features_f32a(o, P[o], out=feat[plan.rr_row[o] * k: plan.rr_row[o] * k + k])
+                if ws == plan.wslot[plan.order[0]]:   # first scorer group: every object's candidates in one launch
+                    ctx.features_multi([(o, P[o], feat[plan.rr_row[o] * k: plan.rr_row[o] * k + k]) for o in plan.order])
                 ctx.pool_f32a(ws, feat[r0: r0 + len(members) * k], out=rr["pooled"][r0: r0 + len(members) * k])
             else:
                 for o in members:

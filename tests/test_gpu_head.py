@@ -332,6 +332,44 @@ def test_frame_scorer_and_shim_models_do_not_clobber_each_others_weights(ctx):
         assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-6
 
 
+@pytest.mark.parametrize("fmt", ["bf16", "f32", "split"])
+def test_features_multi_equals_per_object_launches(ctx, fmt):
+    """One launch over several objects (different cloud sizes, a kept-index list, a device-side count, an empty
+    segment, 40 segments = two launches) == zs_features object by object, bit for bit."""
+    from ossid_code_b200.engine import poses_to_rt12
+    sc = syn.make_scene(47, "lmo", n_obj=4, n_pts=300, n_hypo=90)
+    for key in ("model_points", "model_colors", "model_normals"):
+        sc["objects"][1][key] = sc["objects"][1][key][:77].copy()
+        sc["objects"][2][key] = np.concatenate([sc["objects"][2][key]] * 5)[:1400].copy()
+    ctx.set_frame_u8(sc["img"], sc["depth"], glue.K2meta(sc["cam_K"]))
+    p12 = []
+    for o, ob in enumerate(sc["objects"]):
+        ctx.set_object(o, ob["model_points"], ob["model_colors"], ob["model_normals"])
+        p12.append(poses_to_rt12(ob["pose_hypos"], ctx.device))
+
+    def empty(n, N):
+        if fmt == "split":
+            return torch.zeros((n, 2, N, 8), dtype=torch.bfloat16, device=ctx.device)
+        return torch.zeros((n, N, 8), dtype=torch.float32 if fmt == "f32" else torch.bfloat16, device=ctx.device)
+
+    keep = torch.arange(1, 90, 4, dtype=torch.int32, device=ctx.device)
+    n_dev = torch.tensor([13], dtype=torch.int32, device=ctx.device)
+    outs = [empty(90, 300), empty(len(keep), 77), empty(90, 1400), empty(20, 300), empty(0, 300)]
+    ctx.features_multi([(0, p12[0], outs[0]), (1, p12[1], outs[1], keep), (2, p12[2], outs[2]),
+                        (3, p12[3][5:], outs[3], None, n_dev, 5), (0, p12[0][:0], outs[4])])
+    ref0 = ctx.features(0, p12[0], out=empty(90, 300))[0]
+    ref1 = ctx.features(1, p12[1], keep_idx=keep, out=empty(len(keep), 77))[0]
+    ref2 = ctx.features(2, p12[2], out=empty(90, 1400))[0]
+    ref3 = empty(20, 300)
+    ctx.features(3, p12[3][5:13].contiguous(), out=ref3[:8])           # entries [5, 13) of a list of 13; rows beyond stay untouched
+    for i, (got, ref) in enumerate(zip(outs, (ref0, ref1, ref2, ref3))):
+        assert torch.equal(got, ref), f"segment {i}"
+    many = [empty(3, 300) for _ in range(40)]
+    ctx.features_multi([(0, p12[0][i: i + 3], many[i]) for i in range(40)])
+    for i in range(40):
+        assert torch.equal(many[i], ref0[i: i + 3]), f"segment {i} of 40"
+
+
 def test_more_objects_than_cloud_slots_raises(ctx):
     sc = syn.make_scene(19, "tiny", n_obj=1, n_pts=32, n_hypo=4)
     fs = scoring.FrameScorer([weights.seeded_folded(0)], device=0, k=2)
