@@ -215,6 +215,8 @@ def config_for(args, world, scaling):
     return {"workload": f"{args.workload}: {desc}", "hypotheses_per_step": n_obj * per_gpu * mult * n_frames,
             "frames_per_step": n_frames, "objects": n_obj, "points_per_object": n_pts, "topk": args.k,
             "inconst_ratio_th": args.inconst_th,
+            "kernels": ("fused projection+gather+features+MLP+max-pool kernel" if (args.precision == "bf16" and not args.no_fuse
+                        and args.inconst_th >= 100) else "zs_features -> zs_pool (features through HBM)"),
             "parallelism": (f"hypothesis-sharded x{world}, one all-gather of top-k records" if world > 1 else "single GPU"),
             "l2": "feature chunks of 32768 hypotheses x 1000 pts (>= 0.5 GB) exceed the 126 MB L2; no flush needed",
             "weights": "seeded random (no checkpoint is published)"}
@@ -275,7 +277,7 @@ class Runner:
         self.args, self.sc, self.dev = args, sc, torch.device("cuda", local)
         w = [weights.seeded_folded(0), weights.seeded_folded(1)]
         self.fs = scoring.FrameScorer(w, device=local, precision=args.precision, inconst_ratio_th=args.inconst_th,
-                                      k=args.k, rerank=not args.no_rerank)
+                                      k=args.k, rerank=not args.no_rerank, fused=not args.no_fuse)
         self.fs.forced_rank_world = world_view      # (0, 1): score the whole frame on this rank alone, no collective
         self.weight_of = (lambda o: o % 2)          # two scorers keyed on object parity, online_learning.py:461-463
         self.frame = None
@@ -335,6 +337,8 @@ def main():
                     help="N>1: fixed frames that are additionally sharded over the ranks and checked against rank 0 "
                          "scoring them alone (sub-records `strong`, `strong_c2`); empty = skip")
     ap.add_argument("--no-rerank", action="store_true", help="skip the fp32-accurate re-scoring of the top-k candidates")
+    ap.add_argument("--no-fuse", action="store_true",
+                    help="bf16 path: zs_features + zs_pool as two kernels (features through HBM) instead of the fused kernel")
     ap.add_argument("--k", type=int, default=8)
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="hypotheses per step of the CPU arm (0 = one whole object of the workload)")

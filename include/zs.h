@@ -183,6 +183,15 @@ ZS_API int zs_pool(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtyp
 ZS_API int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n, int precision, float* scores_out,
             void* stream);
 
+/* zs_features + zs_pool (bf16 tensor-core path) in ONE kernel: the producer warps of the MLP kernel project, gather and
+ * featurise each 128-point tile themselves and hand it to the tensor cores through shared memory, so the feature rows
+ * never travel through HBM.  The hypothesis list is the concatenation of n_seg segments: segment i = n_hyp[i]
+ * hypotheses of the cloud in obj_slots[i] with poses[i] [dev] float32 [n_hyp[i]][12] (obj_slots / poses / n_hyp are
+ * [host] arrays); all clouds of a call have the same number of points (>= 128).  pooled_out [dev] float32
+ * [sum n_hyp][1024], bit-identical to zs_features(ZS_BF16) followed by zs_pool. */
+ZS_API int zs_pool_fused(zs_ctx* ctx, int weight_slot, int n_seg, const int32_t* obj_slots, const float* const* poses,
+                  const int32_t* n_hyp, float* pooled_out, void* stream);
+
 /* Diagnostic twin of zs_pool for ZS_BF16 / ZS_BF16_SPLIT features: additionally dumps the activations of layers 1
  * and 2 as the next layer reads them (h1_out [dev] float32 [n*n_pts][64], h2_out [dev] float32 [n*n_pts][128];
  * either may be NULL).  Used by the parity tests to localise a tensor-core mismatch. */

@@ -40,6 +40,7 @@ SIGNATURES = {
     "zs_split_features": (_i, [_p, _p, _i, _i, _p, _p]),
     "zs_pool": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "zs_head": (_i, [_p, _i, _p, _i, _i, _p, _p]),
+    "zs_pool_fused": (_i, [_p, _i, _i, _p, _p, _p, _p, _p]),
     "zs_pool_debug": (_i, [_p, _i, _p, _i, _i, _i, _p, _p, _p, _p]),
     "zs_pose_errors": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _p]),
     "zs_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),

@@ -167,3 +167,73 @@ __device__ __forceinline__ void zs_project(const zs_cam& cam, float x, float y, 
     ur = rintf(xadd(xmul(xdiv(x, z), cam.fx), cam.cx));
     vr = rintf(xadd(xmul(xdiv(y, z), cam.fy), cam.cy));
 }
+
+// ---------------------------------------------------------------------------------------
+// Per-point featurisation of the hot path, shared by the feature kernels (zs_features.cu) and by the producer warps of
+// the fused tensor-core scorer (zs_score_tc.cu) so that both write bit-identical rows.
+// Phase 1 (exact arithmetic): projection, validity, the pixel to gather.  Phase 2: residual features
+// [u_n, v_n, dH, dS, dV, dD, ncos]; the cosine may use FMA / MUFU (a 1e-4 feature).
+// ---------------------------------------------------------------------------------------
+#define ZS_FLT_MAX 3.402823466e38f    // 0 < z <= FLT_MAX, i.e. finite (oracle: z < inf)
+
+struct zs_obj_view {
+    const float4* pA;   // {px, py, pz, Hm}
+    const float4* pB;   // {nx, ny, nz, Sm}
+    const float* pV;    // Vm
+    int n_pts;
+};
+
+__device__ __forceinline__ float zs_rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// -> camera-frame point, rounded pixel (0,0 when invalid), validity, linear pixel index of the gather
+__device__ __forceinline__ void zs_feat_phase1(const zs_pose& T, const zs_cam& cam, const float4& a, float& x, float& y,
+                                               float& z, float& uf, float& vf, bool& valid, int& pix) {
+    float ur, vr;
+    zs_transform(T, a.x, a.y, a.z, x, y, z);
+    zs_project(cam, x, y, z, ur, vr);
+    valid = (z > 0.f) && (z <= ZS_FLT_MAX) && (ur >= 0.f) && (ur < (float)cam.W) && (vr >= 0.f) && (vr < (float)cam.H);
+    uf = valid ? ur : 0.f;
+    vf = valid ? vr : 0.f;
+    pix = (int)vf * cam.W + (int)uf;
+}
+
+// px = the gathered frame pixel {d_obs, H, S, V}; a, b, vm = the model point; f[0..6] = the seven feature channels
+__device__ __forceinline__ void zs_feat_phase2(const zs_pose& T, const zs_cam& cam, const float4& a, const float4& b, float vm,
+                                               const float4& px, float x, float y, float z, float uf, float vf,
+                                               float (&f)[7]) {
+    const float nx = fmaf(T.r[0], b.x, fmaf(T.r[1], b.y, T.r[2] * b.z));
+    const float ny = fmaf(T.r[4], b.x, fmaf(T.r[5], b.y, T.r[6] * b.z));
+    const float nz = fmaf(T.r[8], b.x, fmaf(T.r[9], b.y, T.r[10] * b.z));
+    const float dot = -fmaf(x, nx, fmaf(y, ny, z * nz));
+    const bool vd = (px.x > 0.f) && (px.x <= ZS_FLT_MAX);
+    float dH = px.y - a.w;
+    dH = dH > 0.5f ? dH - 1.0f : dH;
+    dH = dH < -0.5f ? dH + 1.0f : dH;
+    f[0] = (uf - cam.cx) * cam.inv_fx;
+    f[1] = (vf - cam.cy) * cam.inv_fy;
+    f[2] = dH;
+    f[3] = px.z - b.w;
+    f[4] = px.w - vm;
+    f[5] = vd ? xsub(px.x, z) : 0.f;
+    // cos of the angle between the viewing ray and the rotated normal (python/ossid/datasets/ycbv_object.py:74)
+    const float c = dot * zs_rsqrt_fast(fmaf(x, x, fmaf(y, y, z * z))) * zs_rsqrt_fast(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+    f[6] = (fabsf(c) <= ZS_FLT_MAX) ? c : 0.f;      // NaN / inf (degenerate pose) -> 0
+}
+
+__device__ __forceinline__ uint32_t zs_pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// the 16-byte bf16 row of a point (zeros when its projection is invalid)
+__device__ __forceinline__ uint4 zs_feat_row_bf16(const float (&f)[7], bool valid) {
+    uint4 v;
+    v.x = zs_pack_bf16x2(f[0], f[1]); v.y = zs_pack_bf16x2(f[2], f[3]);
+    v.z = zs_pack_bf16x2(f[4], f[5]); v.w = zs_pack_bf16x2(f[6], 0.f);
+    if (!valid) v = make_uint4(0u, 0u, 0u, 0u);
+    return v;
+}

@@ -19,12 +19,7 @@ constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kMaxThreads = 1024;
 constexpr float kFltMax = 3.402823466e38f;   // 0 < z <= FLT_MAX, i.e. finite (oracle: z < inf)
 
-struct obj_view {
-    const float4* pA;
-    const float4* pB;
-    const float* pV;
-    int n_pts;
-};
+using obj_view = zs_obj_view;
 
 // bytes of shared memory taken by a staged model cloud, rounded so that what follows is 16-byte aligned
 __host__ __device__ __forceinline__ size_t cloud_smem(int n_pts) { return ((size_t)n_pts * 36 + 15) & ~(size_t)15; }
@@ -234,7 +229,6 @@ __device__ __forceinline__ void hot_units(const obj_view& o, const zs_cam& cam, 
     constexpr int kIlp = 2, kChunk = 256;
     const int lane = threadIdx.x & 31;
     const int N = o.n_pts;
-    const float fW = (float)cam.W, fH = (float)cam.H;
     const int n_chunks = (N + kChunk - 1) / kChunk;
     const long long n_units = (long long)n_keep * n_chunks;
     for (long long u = first_unit; u < n_units; u += n_warps) {
@@ -251,42 +245,22 @@ __device__ __forceinline__ void hot_units(const obj_view& o, const zs_cam& cam, 
             bool valid[kIlp];
 #pragma unroll
             for (int j = 0; j < kIlp; ++j) {                 // phase 1: exact projection, issue the gather
+                int pix;
                 q[j] = min(p0 + j * 32 + lane, p_end - 1);
                 a[j] = kSmem ? sA[q[j]] : __ldg(sA + q[j]);
-                float ur, vr;
-                zs_transform(T, a[j].x, a[j].y, a[j].z, x[j], y[j], z[j]);
-                zs_project(cam, x[j], y[j], z[j], ur, vr);
-                valid[j] = (z[j] > 0.f) && (z[j] <= kFltMax) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
-                uf[j] = valid[j] ? ur : 0.f;
-                vf[j] = valid[j] ? vr : 0.f;
-                px[j] = __ldg(frame + ((int)vf[j] * cam.W + (int)uf[j]));   // {d_obs, H, S, V}; pixel 0 when invalid
+                zs_feat_phase1(T, cam, a[j], x[j], y[j], z[j], uf[j], vf[j], valid[j], pix);
+                px[j] = __ldg(frame + pix);                  // {d_obs, H, S, V}; pixel 0 when invalid
             }
 #pragma unroll
             for (int j = 0; j < kIlp; ++j) {                 // phase 2: residual features, store
                 const int p = p0 + j * 32 + lane;
                 const float4 b = kSmem ? sB[q[j]] : __ldg(sB + q[j]);
                 const float vm = kSmem ? sV[q[j]] : __ldg(sV + q[j]);
-                const float nx = fmaf(T.r[0], b.x, fmaf(T.r[1], b.y, T.r[2] * b.z));
-                const float ny = fmaf(T.r[4], b.x, fmaf(T.r[5], b.y, T.r[6] * b.z));
-                const float nz = fmaf(T.r[8], b.x, fmaf(T.r[9], b.y, T.r[10] * b.z));
-                const float dot = -fmaf(x[j], nx, fmaf(y[j], ny, z[j] * nz));
-                const bool vd = (px[j].x > 0.f) && (px[j].x <= kFltMax);
-                float dH = px[j].y - a[j].w;
-                dH = dH > 0.5f ? dH - 1.0f : dH;
-                dH = dH < -0.5f ? dH + 1.0f : dH;
-                const float f0 = (uf[j] - cam.cx) * cam.inv_fx;
-                const float f1 = (vf[j] - cam.cy) * cam.inv_fy;
-                const float f3 = px[j].z - b.w;
-                const float f4 = px[j].w - vm;
-                const float f5 = vd ? xsub(px[j].x, z[j]) : 0.f;
-                const float c = dot * rsqrt_fast(fmaf(x[j], x[j], fmaf(y[j], y[j], z[j] * z[j]))) *
-                                rsqrt_fast(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
-                const float f6 = (fabsf(c) <= kFltMax) ? c : 0.f;      // NaN / inf (degenerate pose) -> 0
+                float f[7];
+                zs_feat_phase2(T, cam, a[j], b, vm, px[j], x[j], y[j], z[j], uf[j], vf[j], f);
+                const float f0 = f[0], f1 = f[1], dH = f[2], f3 = f[3], f4 = f[4], f5 = f[5], f6 = f[6];
                 if (kFmt == ZS_BF16) {
-                    uint4 v;
-                    v.x = pack_bf16x2(f0, f1); v.y = pack_bf16x2(dH, f3);
-                    v.z = pack_bf16x2(f4, f5); v.w = pack_bf16x2(f6, 0.f);
-                    if (!valid[j]) v = make_uint4(0u, 0u, 0u, 0u);
+                    const uint4 v = zs_feat_row_bf16(f, valid[j]);
                     if (p < p_end) st_cs_u4(reinterpret_cast<uint4*>(feat_out) + row + p, v);
                 } else if (kFmt == ZS_BF16_SPLIT) {
                     uint4 h, l;

@@ -63,7 +63,25 @@ namespace {
 constexpr int kTile = 128;               // points per CTA per pair-tile
 constexpr int kPairTile = 2 * kTile;     // points per pair-tile
 constexpr int kThreadsTc = 320;
+constexpr int kThreadsFused = 352;       // + warp 10: the second feature-producer warp of the fused kernel
 constexpr int kStages = 3;
+
+// Fused variant (K1 inside K2): instead of bulk-copying bf16 feature rows that zs_features wrote to HBM, two producer
+// warps per CTA project / gather / featurise the 128 points of each half-tile themselves (the per-point code of
+// zs_common.cuh, so the rows are bit-identical) and store them straight into the X stage.  The hypothesis list of a
+// launch may span several objects of one cloud size: segment g covers rows [first_row[g], first_row[g+1]).
+constexpr int kMaxFusedSegs = 32;
+struct fused_seg {
+    zs_obj_view o;          // model cloud (global memory; 36 B per point, read coalesced through L1 / L2)
+    const float* poses;     // poses of this segment: row h of the launch is pose h - first_row
+    int first_row, pad_;
+};
+struct fused_args {
+    zs_cam cam;
+    const float4* frame;    // packed frame {depth, H, S, V}
+    int n_seg, pad_;
+    fused_seg seg[kMaxFusedSegs];
+};
 
 // ---- shared-memory map (bytes from a 1024-aligned base) ---------------------------------------
 constexpr uint32_t kSmW3 = 0;                          // 4 blocks x 2 k-halves x 16 KB
@@ -105,10 +123,13 @@ constexpr size_t kImgW3Half = 131072, kImgW2 = 2 * kImgW3Half, kImgW1 = kImgW2 +
 using namespace zs_tc;
 
 // ---- the kernel ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsTc, 1)
+template <bool kFused>
+__global__ void __launch_bounds__(kFused ? kThreadsFused : kThreadsTc, 1)
 zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t* __restrict__ wimg,
             const float* __restrict__ wf32, float* __restrict__ pooled, float* __restrict__ dbg_h1,
-            float* __restrict__ dbg_h2, const int32_t* __restrict__ n_dev, int n_off) {
+            float* __restrict__ dbg_h2, const int32_t* __restrict__ n_dev, int n_off,
+            const __grid_constant__ fused_args fa) {
+    constexpr int kThreadsK = kFused ? kThreadsFused : kThreadsTc;
     n = zs_dyn_count(n_dev, n_off, n);          // zs_set_dynamic_count: the count may live on the device
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -127,7 +148,8 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
         mbar_init(bar(BAR_W_FULL), 1);
         mbar_init(bar(BAR_WP_FULL), 1);
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(bar(BAR_X_FULL + s), 1); mbar_init(bar(BAR_X_EMPTY + s), 1); mbar_init(bar(BAR_XP_FULL + s), 1);
+            // fused: the leader's X_FULL collects one arrival per producer warp of the pair (2 + 2); XP_FULL is unused
+            mbar_init(bar(BAR_X_FULL + s), kFused ? 4 : 1); mbar_init(bar(BAR_X_EMPTY + s), 1); mbar_init(bar(BAR_XP_FULL + s), 1);
         }
         mbar_init(bar(BAR_D1_FULL), 1); mbar_init(bar(BAR_D2_FULL), 1);
         mbar_init(bar(BAR_A2_FULL), 8);                                   // one arrival per epilogue warp of the pair (4 + 4)
@@ -136,10 +158,10 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // zero the feature stages and the zero block (stale bytes must be finite), stage the small biases
-    for (int i = tid; i < (int)((kStages + 1) * 2048 / 16); i += kThreadsTc)
+    for (int i = tid; i < (int)((kStages + 1) * 2048 / 16); i += kThreadsK)
         reinterpret_cast<uint4*>(sm + kSmX)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 64; i += kThreadsTc) reinterpret_cast<float*>(sm + kSmB1)[i] = wf32[ZS_OFF_B1 + i];
-    for (int i = tid; i < 128; i += kThreadsTc) reinterpret_cast<float*>(sm + kSmB2)[i] = wf32[ZS_OFF_B2 + i];
+    for (int i = tid; i < 64; i += kThreadsK) reinterpret_cast<float*>(sm + kSmB1)[i] = wf32[ZS_OFF_B1 + i];
+    for (int i = tid; i < 128; i += kThreadsK) reinterpret_cast<float*>(sm + kSmB2)[i] = wf32[ZS_OFF_B2 + i];
     fence_proxy_async();
     if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmTmemPtr), "r"(kTmemCols) : "memory");
@@ -161,7 +183,62 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
         return (long long)(pair + j * n_pairs) * N + (long long)(s0 + kTile <= N ? s0 : (N >= kTile ? N - kTile : 0));
     };
 
-    if (warp == 8) {
+    if (kFused && (warp == 8 || warp == 10)) {
+        // ===== feature producers (fused): warp 8 -> rows [0,64) of the half-tile, warp 10 -> rows [64,128) ==========
+        if (warp == 8 && lane == 0) {                           // the weights still arrive by bulk copy, once
+            mbar_expect_tx(bar(BAR_W_FULL), 131072 + 8192 + 1024);
+            for (int c = 0; c < 8; ++c)
+                bulk_g2s(sbase + kSmW3 + c * 16384, wimg + (size_t)rank * kImgW3Half + (size_t)c * 16384, 16384, bar(BAR_W_FULL));
+            bulk_g2s(sbase + kSmW2, wimg + kImgW2 + (size_t)rank * 8192, 8192, bar(BAR_W_FULL));
+            bulk_g2s(sbase + kSmW1, wimg + kImgW1 + (size_t)rank * 1024, 1024, bar(BAR_W_FULL));
+            if (rank != 0) { mbar_wait(bar(BAR_W_FULL), 0); mbar_arrive_leader(leader_addr(bar(BAR_WP_FULL))); }
+        }
+        __syncwarp();
+        const int row0 = warp == 8 ? 0 : 64;
+        const uint32_t x_full = leader_addr(bar(BAR_X_FULL));
+        const float4* __restrict__ frame = fa.frame;
+        zs_pose P;
+        const float4 *pA = nullptr, *pB = nullptr;
+        const float* pV = nullptr;
+        for (int i = 0; i < total; ++i) {
+            const int s = i % kStages, j = i / T, tt = i - j * T;
+            if (tt == 0) {                                      // new hypothesis: its object (segment) and pose
+                const int h = pair + j * n_pairs;
+                int g = 0;
+                while (g + 1 < fa.n_seg && fa.seg[g + 1].first_row <= h) ++g;
+                pA = fa.seg[g].o.pA; pB = fa.seg[g].o.pB; pV = fa.seg[g].o.pV;
+                P = zs_load_pose(fa.seg[g].poses, h - fa.seg[g].first_row);
+            }
+            const int s0 = tt * kPairTile + rank * kTile;
+            const int p0 = (s0 + kTile <= N ? s0 : N - kTile) + row0;      // first of this warp's 64 points (N >= kTile)
+            float4 a[2], px[2];
+            float x[2], y[2], z[2], uf[2], vf[2];
+            bool valid[2];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {                    // phase 1: exact projection, issue the frame gather
+                int pix;
+                a[jj] = __ldg(pA + p0 + jj * 32 + lane);
+                zs_feat_phase1(P, fa.cam, a[jj], x[jj], y[jj], z[jj], uf[jj], vf[jj], valid[jj], pix);
+                px[jj] = __ldg(frame + pix);
+            }
+            uint4 v[2];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {                    // phase 2: residual features -> the 16-byte bf16 row
+                const float4 b = __ldg(pB + p0 + jj * 32 + lane);
+                const float vm = __ldg(pV + p0 + jj * 32 + lane);
+                float f[7];
+                zs_feat_phase2(P, fa.cam, a[jj], b, vm, px[jj], x[jj], y[jj], z[jj], uf[jj], vf[jj], f);
+                v[jj] = zs_feat_row_bf16(f, valid[jj]);
+            }
+            mbar_wait(bar(BAR_X_EMPTY + s), ((i / kStages) & 1) ^ 1);      // layer 1 of pair-tile i-3 has read this stage
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+                *reinterpret_cast<uint4*>(sm + kSmX + s * 2048 + (row0 + jj * 32 + lane) * 16) = v[jj];
+            fence_proxy_async();                                // generic-proxy stores -> visible to the MMA's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(x_full + 8u * s);
+        }
+    } else if (!kFused && warp == 8) {
         // ===== bulk-copy producer =================================================================
         if (lane == 0) {
             mbar_expect_tx(bar(BAR_W_FULL), 131072 + 8192 + 1024);
@@ -232,7 +309,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
                 if (i < total) {
                     const int s = i % kStages;
                     PROF_WAIT(3, mbar_wait(bar(BAR_X_FULL + s), (i / kStages) & 1));
-                    PROF_WAIT(3, mbar_wait(bar(BAR_XP_FULL + s), (i / kStages) & 1));
+                    if (!kFused) PROF_WAIT(3, mbar_wait(bar(BAR_XP_FULL + s), (i / kStages) & 1));
                     tc_fence_after();
                     const uint32_t xa = sbase + kSmX + s * 2048;
                     tc_mma(tmem + kColD1, desc_at(desc_lo(xa, (sbase + kSmZero) - xa), hi_x, 0), desc_at(w1_lo, hi_x, 0), idesc_l1, 0);
@@ -309,7 +386,7 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             if (lane == 0) mbar_arrive_leader(a3_full + 8u * buf);
         }
         if (tid == 0) PROF_DUMP(8, 3);
-    } else {
+    } else if (warp < 8) {
         // ===== max-pool epilogue: D3[channel lane][point column] -> running max -> pooled ===========
         // Columns of a layer-3 accumulator of point half hh: 0-63 = points 64*hh.. of the leader's half-tile,
         // 64-127 = points 64*hh.. of the peer's half-tile (the N side concatenates the two CTAs' operand rows).
@@ -408,10 +485,11 @@ int zs_tc_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st) {
 
 void zs_tc_destroy(zs_ctx*) {}
 
+template <bool kFused>
 static int launch_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, int n_pts, float* pooled,
-                     float* dbg_h1, float* dbg_h2, cudaStream_t st) {
+                     float* dbg_h1, float* dbg_h2, const fused_args& fa, cudaStream_t st) {
     const zs_weights& w = ctx->w[slot];
-    ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmAlloc));
+    ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_mlp_tc<kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmAlloc));
 #ifdef ZS_TC_PROF
     { const char* e = getenv("ZS_TC_EXPERIMENT"); int v = e ? atoi(e) : 0; cudaMemcpyToSymbolAsync(g_exp, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st); }
 #endif
@@ -419,7 +497,7 @@ static int launch_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, in
     if (grid > 2 * n) grid = 2 * n;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    cfg.blockDim = dim3(kThreadsTc, 1, 1);
+    cfg.blockDim = dim3(kFused ? kThreadsFused : kThreadsTc, 1, 1);
     cfg.dynamicSmemBytes = kSmAlloc;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -429,14 +507,62 @@ static int launch_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, in
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ZS_CUDA(ctx, cudaLaunchKernelEx(&cfg, zs_k_mlp_tc, feat, n, n_pts, reinterpret_cast<const uint8_t*>(w.bf16),
-                                    (const float*)w.f32, pooled, dbg_h1, dbg_h2, ctx->dyn_n, ctx->dyn_off));
+    ZS_CUDA(ctx, cudaLaunchKernelEx(&cfg, zs_k_mlp_tc<kFused>, feat, n, n_pts, reinterpret_cast<const uint8_t*>(w.bf16),
+                                    (const float*)w.f32, pooled, dbg_h1, dbg_h2, kFused ? nullptr : ctx->dyn_n,
+                                    kFused ? 0 : ctx->dyn_off, fa));
     ZS_LAUNCHED(ctx);
     return ZS_OK;
 }
 
 int zs_score_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, int n_pts, float* pooled, cudaStream_t st) {
-    return launch_tc(ctx, slot, feat, n, n_pts, pooled, nullptr, nullptr, st);
+    return launch_tc<false>(ctx, slot, feat, n, n_pts, pooled, nullptr, nullptr, fused_args{}, st);
+}
+
+// Fused projection + gather + features + shared MLP + max-pool (bf16): the hypothesis list is the concatenation of the
+// segments (segment i: n_hyp[i] hypotheses of the cloud in obj_slots[i], poses [dev] float32 [n_hyp[i]][12]).
+extern "C" int zs_pool_fused(zs_ctx* ctx, int weight_slot, int n_seg, const int32_t* obj_slots, const float* const* poses,
+                             const int32_t* n_hyp, float* pooled_out, void* stream) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (weight_slot < 0 || weight_slot >= ZS_MAX_WEIGHT_SLOTS || !ctx->w[weight_slot].set)
+        return zs_fail(ctx, ZS_ERR_STATE, "weight slot %d not set", weight_slot);
+    if (n_seg < 0 || (n_seg > 0 && (!obj_slots || !poses || !n_hyp || !pooled_out)))
+        return zs_fail(ctx, ZS_ERR_INVALID, "zs_pool_fused arguments");
+    if (ctx->dyn_n) return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "device-side counts: use zs_features + zs_pool");
+    if (!ctx->frame.set) return zs_fail(ctx, ZS_ERR_STATE, "frame not set");
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const zs_frame& f = ctx->frame;
+    size_t row = 0;
+    int i = 0, n_pts = 0;
+    while (i < n_seg) {                                   // launches of at most kMaxFusedSegs segments
+        fused_args fa = {};
+        fa.cam = zs_cam{f.fx, f.fy, f.cx, f.cy, f.inv_fx, f.inv_fy, f.H, f.W};
+        fa.frame = f.packed;
+        int n = 0;
+        for (; i < n_seg && fa.n_seg < kMaxFusedSegs; ++i) {
+            if (n_hyp[i] == 0) continue;
+            const int slot = obj_slots[i];
+            if (slot < 0 || slot >= ZS_MAX_OBJECTS || ctx->obj[slot].n_pts == 0)
+                return zs_fail(ctx, ZS_ERR_STATE, "object slot %d not set", slot);
+            const zs_object& ob = ctx->obj[slot];
+            if (n_pts == 0) n_pts = ob.n_pts;
+            if (ob.n_pts != n_pts || n_pts < kTile)
+                return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "fused scoring needs one cloud size >= %d per call (got %d and %d)",
+                               kTile, n_pts, ob.n_pts);
+            if (n_hyp[i] < 0 || !poses[i] || ((uintptr_t)poses[i] & 15))
+                return zs_fail(ctx, ZS_ERR_INVALID, "segment %d: n_hyp %d / poses alignment", i, n_hyp[i]);
+            fused_seg& g = fa.seg[fa.n_seg++];
+            g.o = zs_obj_view{ob.pA, ob.pB, ob.pV, ob.n_pts};
+            g.poses = poses[i];
+            g.first_row = n;
+            n += n_hyp[i];
+        }
+        if (n == 0) continue;
+        int rc = launch_tc<true>(ctx, weight_slot, nullptr, n, n_pts, pooled_out + row * 1024, nullptr, nullptr, fa,
+                                 (cudaStream_t)stream);
+        if (rc) return rc;
+        row += (size_t)n;
+    }
+    return ZS_OK;
 }
 
 // Diagnostic entry point: as zs_pool (bf16 or split-bf16 features) but also dumps the activations of layers 1 and 2 as
@@ -451,5 +577,6 @@ extern "C" int zs_pool_debug(zs_ctx* ctx, int weight_slot, const void* feat, int
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (feat_dtype == ZS_BF16_SPLIT)
         return zs_score_tc3(ctx, weight_slot, feat, n, n_pts, pooled_out, h1_out, h2_out, (cudaStream_t)stream);
-    return launch_tc(ctx, weight_slot, (const __nv_bfloat16*)feat, n, n_pts, pooled_out, h1_out, h2_out, (cudaStream_t)stream);
+    return launch_tc<false>(ctx, weight_slot, (const __nv_bfloat16*)feat, n, n_pts, pooled_out, h1_out, h2_out, fused_args{},
+                            (cudaStream_t)stream);
 }

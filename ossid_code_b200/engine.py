@@ -311,6 +311,21 @@ class ZsContext:
                                   self._stream()), "zs_pool")
         return pooled
 
+    def pool_fused(self, wslot: int, segments, out: torch.Tensor) -> torch.Tensor:
+        """``zs_pool_fused``: featurise + shared MLP + max-pool in one kernel.  ``segments``: [(slot, poses12), ...] of one
+        cloud size; ``out`` (sum of hypotheses, 1024) float32."""
+        segs = [sg for sg in segments if sg[1].shape[0] > 0]
+        n = len(segs)
+        if n == 0:
+            return out
+        slots = (C.c_int32 * n)(*[sg[0] for sg in segs])
+        poses = (C.c_void_p * n)(*[sg[1].data_ptr() for sg in segs])
+        counts = (C.c_int32 * n)(*[sg[1].shape[0] for sg in segs])
+        if out.shape[0] < sum(sg[1].shape[0] for sg in segs):
+            raise ValueError("pool_fused: output has fewer rows than hypotheses")
+        self._ck(self.lib.zs_pool_fused(self.h, wslot, n, slots, poses, counts, out.data_ptr(), self._stream()), "zs_pool_fused")
+        return out
+
     def head(self, wslot: int, pooled: torch.Tensor, tensor_cores: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(n,1024) pooled -> (n,) scores; tensor_cores=True: tf32 tcgen05 GEMMs, False: fp32 CUDA cores."""
         n = pooled.shape[0]

@@ -170,7 +170,8 @@ class FrameScorer:
 
     def __init__(self, weights: Sequence[dict], device: Optional[int] = None, precision: str = "bf16",
                  inconst_ratio_th: float = 100.0, k: int = 8, chunk: int = 32768, group=None,
-                 ctx: Optional[ZsContext] = None, reorder_points: bool = True, rerank: Optional[bool] = None):
+                 ctx: Optional[ZsContext] = None, reorder_points: bool = True, rerank: Optional[bool] = None,
+                 fused: bool = True):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         if len(weights) > MAX_WEIGHT_SLOTS:
@@ -182,6 +183,9 @@ class FrameScorer:
         self.split = precision == "fp32"      # fp32-accurate: split-bf16 features + the 3-term tcgen05 scorer + the fp32 head
         self.th, self.k, self.chunk, self.group = float(inconst_ratio_th), int(k), int(chunk), group
         self.rerank = (precision == "bf16") if rerank is None else bool(rerank and precision == "bf16")
+        # bf16 path without pre-filter: features are computed inside the MLP kernel (zs_pool_fused) instead of being
+        # written to HBM by zs_features and read back; fused=False keeps the two-kernel sequence (bit-identical results)
+        self.fused = bool(fused) and precision == "bf16"
         self._weights = list(weights)
         self._wtoken = [object() for _ in weights]       # ownership tokens of this scorer's weight slots
         self.n_weights = len(weights)
@@ -450,6 +454,12 @@ class FrameScorer:
             for ws in sorted({res[o]["wslot"] for o in order}):
                 members = [o for o in order if res[o]["wslot"] == ws]
                 lo, hi = offs[members[0]], offs[members[-1]] + n_keeps[members[-1]]
+                if self.fused and N >= 128:
+                    # projection + gather + features + MLP + max-pool of the scorer's whole hypothesis list in one kernel
+                    t = self._mark("pool", (hi - lo) * N)
+                    ctx.pool_fused(ws, [(res[o]["slot"], res[o]["poses12"]) for o in members], out=self._pooled[lo:hi])
+                    self._mark(None, 0, t)
+                    continue
                 for cs in range(lo, hi, self.chunk):
                     ce = min(cs + self.chunk, hi)
                     feat = self._feat_buf(ce - cs, N, min(self.chunk, hi - lo))

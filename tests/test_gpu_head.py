@@ -370,6 +370,39 @@ def test_features_multi_equals_per_object_launches(ctx, fmt):
         assert torch.equal(many[i], ref0[i: i + 3]), f"segment {i} of 40"
 
 
+@pytest.mark.parametrize("n_pts,n_obj,n_hypo", [(1000, 3, 200), (128, 2, 37), (300, 5, 150), (129, 40, 9), (4000, 1, 20)])
+def test_fused_features_and_mlp_equal_the_two_kernel_sequence(ctx, n_pts, n_obj, n_hypo):
+    """zs_pool_fused (producer warps of the tensor-core MLP kernel featurise each tile themselves) == zs_features(bf16)
+    followed by zs_pool, bit for bit: several objects per launch, tail tiles shifted back, more than 32 segments."""
+    from ossid_code_b200.engine import poses_to_rt12
+    sc = syn.make_scene(53, "lmo", n_obj=min(n_obj, 5), n_pts=n_pts, n_hypo=n_hypo)
+    ctx.set_frame_u8(sc["img"], sc["depth"], glue.K2meta(sc["cam_K"]))
+    ctx.set_weights(1, weights.seeded_folded(3))
+    segs, ref = [], []
+    for s in range(n_obj):
+        ob = sc["objects"][s % len(sc["objects"])]
+        ctx.set_object(s, ob["model_points"], ob["model_colors"], ob["model_normals"])
+        p12 = poses_to_rt12(np.roll(ob["pose_hypos"], s, axis=0), ctx.device)
+        segs.append((s, p12))
+        feat, _, _, _ = ctx.features(s, p12, dtype=torch.bfloat16)
+        ref.append(ctx.pool(1, feat))
+    ref = torch.cat(ref)
+    out = torch.full((n_obj * n_hypo + 3, 1024), -7.0, device=ctx.device)
+    ctx.pool_fused(1, segs, out=out)
+    assert torch.equal(out[: n_obj * n_hypo], ref)
+    assert bool((out[n_obj * n_hypo:] == -7.0).all()), "rows beyond the hypothesis list were written"
+
+
+def test_frame_scorer_fused_equals_unfused(ctx):
+    sc = syn.make_scene(59, "ycbv", n_obj=5, n_pts=1000, n_hypo=400)
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    res = []
+    for fused in (True, False):
+        fs = scoring.FrameScorer(ws, device=0, precision="bf16", k=8, fused=fused, rerank=False)
+        res.append(fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=lambda o: o % 2))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
 def test_more_objects_than_cloud_slots_raises(ctx):
     sc = syn.make_scene(19, "tiny", n_obj=1, n_pts=32, n_hypo=4)
     fs = scoring.FrameScorer([weights.seeded_folded(0)], device=0, k=2)
