@@ -122,12 +122,27 @@ ZS_API int zs_mask_count(zs_ctx* ctx, const float* poses, int n, const float* pt
                   int32_t* count_out, void* stream);
 
 /* First half of `ScoreDataset.getPointNetData` (call site zephyr_utils.py:31): number of
- * free-space-violating points per hypothesis.  viol_out [dev] int32 [n]. */
-ZS_API int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, int32_t* viol_out, void* stream);
+ * free-space-violating points per hypothesis.  viol_out [dev] int32 [n].
+ * mask [dev] uint8 H*W (nullable): additionally apply `filterHypoByMask(model_points, meta, poses, mask, mask_th)`
+ * (zephyr_utils.py:49-71; mask_th is a float64 as in Python, the comparison `count / n_pts > th` is made in float64)
+ * in the same pass: a hypothesis that does not project more than mask_th of its points onto
+ * non-zero mask pixels gets viol_out = ZS_VIOL_MASKED (0x7fffffff), which zs_filter never keeps; the kernel abandons
+ * such a hypothesis as soon as its remaining points cannot reach the bar (early-out before the remaining gathers). */
+#define ZS_VIOL_MASKED 0x7fffffff
+ZS_API int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, const uint8_t* mask, double mask_th,
+                  int32_t* viol_out, void* stream);
+
+/* DTOID detections -> binary mask (python/ossid/scripts/online_learning.py:389-405) against the resident frame's depth:
+ * boxes [host] float64 [n_boxes][4] = x1 y1 x2 y2, scores [host] float64 [n_boxes], visited in order; a box with score
+ * < 0.5 is skipped once the mask covers a pixel with depth > 0; the others are grown by expandBox(.., expand_ratio)
+ * (python/ossid/utils/__init__.py:11-16) and filled.  mask_out [dev] uint8 H*W in {0, 1}.  At most 64 boxes. */
+ZS_API int zs_boxes_to_mask(zs_ctx* ctx, const double* boxes, const double* scores, int n_boxes, double expand_ratio,
+                     uint8_t* mask_out, void* stream);
 
 /* Hypothesis pre-filter of getPointNetData (its effect is visible at zephyr_utils.py:39-43;
  * thresholds online_learning.py:174,184): keep h iff viol[h]*100/n_pts < th (th >= 100
- * keeps all); never empty (first minimum kept).  keep_idx_out [dev] int32 [n] ascending,
+ * keeps all); never empty (first minimum kept; entries equal to ZS_VIOL_MASKED are never kept, so the result is
+ * empty when the mask test dropped everything).  keep_idx_out [dev] int32 [n] ascending,
  * n_keep_out [dev] int32[1].  info_out [dev] int32[2] (nullable) = {hypotheses that really passed the test (0 when
  * the never-empty rule supplied the single kept one), violation count of that fallback}: what zs_merge_topk needs to
  * apply the never-empty rule to the object's WHOLE list when the list is sharded over GPUs. */

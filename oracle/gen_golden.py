@@ -62,6 +62,28 @@ def extract_function(path, name):
     return ns[name]
 
 
+def extract_box_mask_block(path):
+    """The reference's box -> mask statements (python/ossid/scripts/online_learning.py:389-405: ``dtoid_mask =
+    np.zeros_like(depth)`` ... the ``for`` over ``final_bbox, final_score``), compiled out of its ``main()``.  Returns a
+    function (depth, final_bbox, final_score, expandBox) -> dtoid_mask that executes exactly those statements."""
+    tree = ast.parse(open(path).read())
+    block = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and node.orelse and isinstance(node.orelse[0], ast.Assign):
+            tgt = node.orelse[0].targets[0]
+            if isinstance(tgt, ast.Name) and tgt.id == "dtoid_mask" and "zeros_like" in ast.unparse(node.orelse[0].value):
+                block = node.orelse
+                break
+    assert block is not None and any(isinstance(n, ast.For) for n in block), "box->mask block not found in the reference"
+    code = compile(ast.Module(body=block, type_ignores=[]), path, "exec")
+
+    def run(depth, final_bbox, final_score, expandBox):
+        ns = {"np": np, "depth": depth, "final_bbox": final_bbox, "final_score": final_score, "expandBox": expandBox}
+        exec(code, ns)
+        return ns["dtoid_mask"]
+    return run
+
+
 def f32exact(a):
     """Round to float32 and back so that the oracle's single f32 cast is lossless."""
     return np.asarray(a, dtype=np.float32).astype(np.float64)
@@ -135,6 +157,30 @@ def gen_mask_filter(ref_glue):
     print("mask_filter.npz: kept", {k: int(v.sum()) for k, v in kept.items()}, "of", len(ob["pose_hypos"]))
 
 
+def gen_boxes_mask():
+    """DTOID boxes -> mask: the reference's own statements (AST-extracted from online_learning.py's main()) and its own
+    expandBox (imported from ossid.utils), on three detection lists: confident + low-score boxes, only low-score boxes,
+    boxes that leave the frame / are empty."""
+    from ossid.utils import expandBox
+    from ossid_code_b200 import synthetic as syn
+    run = extract_box_mask_block(f"{REF}/ossid/scripts/online_learning.py")
+    sc = syn.make_scene(13, "tiny", n_obj=1, n_pts=64, n_hypo=4)
+    depth = sc["depth"]
+    depth[:40, :60] = 0.0                                       # a region without depth: a box there leaves "mask * depth>0" empty
+    cases = {
+        "a": ([[70.2, 30.7, 110.9, 80.1], [10.0, 5.0, 40.0, 30.0], [120.5, 90.0, 150.0, 118.0]], [0.9, 0.3, 0.7]),
+        "b": ([[5.0, 4.0, 30.0, 25.0], [80.0, 60.0, 120.0, 100.0], [20.0, 50.0, 60.0, 90.0]], [0.2, 0.4, 0.1]),
+        "c": ([[-20.0, -10.0, 30.0, 40.0], [140.0, 100.0, 200.0, 160.0], [50.0, 50.0, 50.0, 70.0], [90.0, 20.0, 100.0, 30.0]],
+              [0.6, 0.8, 0.9, 0.45]),
+    }
+    out = {"depth": depth}
+    for tag, (boxes, scores) in cases.items():
+        mask = run(depth, [np.asarray(b) for b in boxes], list(scores), expandBox)
+        out[f"{tag}_boxes"], out[f"{tag}_scores"], out[f"{tag}_mask"] = np.asarray(boxes), np.asarray(scores), mask.astype(np.uint8)
+        print(f"boxes_mask {tag}: {int(mask.sum())} pixels set")
+    np.savez_compressed(os.path.join(OUT, "boxes_mask.npz"), **out)
+
+
 def gen_network_inference(ref_glue):
     from ossid_code_b200 import synthetic as syn, weights
     from oracle import zephyr_oracle as zo
@@ -169,6 +215,7 @@ def main():
     torch.set_num_threads(4)
     gen_projection()
     gen_mask_filter(ref_glue)
+    gen_boxes_mask()
     gen_network_inference(ref_glue)
 
 

@@ -28,7 +28,8 @@ SIGNATURES = {
     "zs_set_weights": (_i, [_p, _i, _p, C.c_size_t, _p]),
     "zs_project_uv": (_i, [_p, _p, _i, _p, _i, _f, _f, _f, _f, _p, _p]),
     "zs_mask_count": (_i, [_p, _p, _i, _p, _i, _f, _f, _f, _f, _p, _i, _i, _p, _p]),
-    "zs_violations": (_i, [_p, _i, _p, _i, _p, _p]),
+    "zs_violations": (_i, [_p, _i, _p, _i, _p, C.c_double, _p, _p]),
+    "zs_boxes_to_mask": (_i, [_p, _p, _p, _i, C.c_double, _p, _p]),
     "zs_filter": (_i, [_p, _p, _i, _i, _f, _p, _p, _p, _p]),
     "zs_reserve": (_i, [_p, _i]),
     "zs_pack_poses": (_i, [_p, _p, _i, _i, _p, _p]),

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -11,6 +12,7 @@
 #include "../../include/zs.h"
 
 #define ZS_SCORE_CHUNK 32768    // hypotheses per scoring chunk (bounds the head's workspace)
+#define ZS_VIOL_MASKED 0x7fffffff   // zs_violations: the hypothesis failed the mask-overlap test (zs_filter never keeps it)
 #define ZS_DEPTH_MARGIN 0.02f   // metres; reference: python/ossid/datasets/ycbv_sift_dataset.py:325
 
 struct zs_frame {

@@ -336,10 +336,15 @@ zs_k_features_multi(const __grid_constant__ feat_segs segs, int n_seg, zs_cam ca
 // ---------------------------------------------------------------------------------------
 // Violation count only (pre-filter pass): exact part of the feature kernel, depth gather only.
 // ---------------------------------------------------------------------------------------
-template <bool kSmem>
+// kMask: the hypothesis must also project at least `mask_min` of its points onto non-zero pixels of `mask`
+// (filterHypoByMask, python/ossid/utils/zephyr_utils.py:49-71; bounds predicate :61-62).  The warp stops working on a
+// hypothesis as soon as the points still to come cannot lift it over that bar (early-out: a hypothesis far from the
+// detector's box is dropped after about half of its projections and without the rest of its depth gathers) and
+// reports ZS_VIOL_MASKED instead of a count.
+template <bool kSmem, bool kMask>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 zs_k_violations(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
-                int n, int32_t* __restrict__ viol_out) {
+                int n, const uint8_t* __restrict__ mask, int mask_min, int32_t* __restrict__ viol_out) {
     extern __shared__ __align__(16) char smem[];
     float4 *sA, *sB;
     float* sV;
@@ -353,23 +358,30 @@ zs_k_violations(obj_view o, zs_cam cam, const float4* __restrict__ frame, const 
     const float* frame_d = reinterpret_cast<const float*>(frame);
     for (int h = warp; h < n; h += n_warps) {
         const zs_pose T = zs_load_pose(poses, h);
-        int viol = 0;
+        int viol = 0, in_mask = 0;
+        bool rejected = false;
         for (int p0 = 0; p0 < N; p0 += 32) {
             const int p = p0 + lane;
-            bool fs = false;
+            bool fs = false, im = false;
             if (p < N) {
                 const float4 a = kSmem ? sA[p] : __ldg(sA + p);
                 float x, y, z, ur, vr;
                 zs_transform(T, a.x, a.y, a.z, x, y, z);
                 zs_project(cam, x, y, z, ur, vr);
-                if ((z > 0.f) && (z <= kFltMax) && (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH)) {
+                const bool in_frame = (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
+                if (kMask && in_frame) im = __ldg(mask + (size_t)(int)vr * cam.W + (int)ur) != 0;   // no z test: zephyr_utils.py:58-66
+                if (in_frame && (z > 0.f) && (z <= kFltMax)) {
                     const float d = __ldg(frame_d + 4 * ((size_t)(int)vr * cam.W + (int)ur));
                     fs = (d > 0.f) && (d <= kFltMax) && (xsub(d, z) > ZS_DEPTH_MARGIN);
                 }
             }
             viol += __popc(__ballot_sync(0xffffffffu, fs));
+            if (kMask) {
+                in_mask += __popc(__ballot_sync(0xffffffffu, im));
+                if (in_mask + max(N - (p0 + 32), 0) < mask_min) { rejected = true; break; }           // warp-uniform
+            }
         }
-        if (lane == 0) viol_out[h] = viol;
+        if (lane == 0) viol_out[h] = rejected ? ZS_VIOL_MASKED : viol;
     }
 }
 
@@ -436,9 +448,11 @@ zs_k_filter(const int32_t* __restrict__ viol, int n, float n_pts_f, float th, in
         bool keep = false;
         if (h < n) {
             const int v = viol[h];
-            keep = (th >= 100.f) || (xdiv(xmul((float)v, 100.f), n_pts_f) < th);
-            const unsigned long long key = ((unsigned long long)(uint32_t)v << 32) | (uint32_t)h;
-            best = key < best ? key : best;
+            if (v != ZS_VIOL_MASKED) {         // dropped by the mask test: never kept, not even by the never-empty rule
+                keep = (th >= 100.f) || (xdiv(xmul((float)v, 100.f), n_pts_f) < th);
+                const unsigned long long key = ((unsigned long long)(uint32_t)v << 32) | (uint32_t)h;
+                best = key < best ? key : best;
+            }
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, keep);
         __syncthreads();               // previous iteration's readers of s_warp / s_total are done
@@ -466,11 +480,12 @@ zs_k_filter(const int32_t* __restrict__ viol, int n, float n_pts_f, float th, in
     __syncthreads();
     if (threadIdx.x == 0) {
         int nk = base_out;
+        const bool have_fallback = s_min != ~0ull;                    // some hypothesis survived the mask test
         if (info_out) {                // what a multi-GPU merge needs to apply the never-empty rule globally
             info_out[0] = base_out;                                   // hypotheses that really passed the test
-            info_out[1] = n > 0 ? (int)(s_min >> 32) : 0;             // violation count of the fallback candidate
+            info_out[1] = have_fallback ? (int)(s_min >> 32) : 0x7fffffff;   // violation count of the fallback candidate
         }
-        if (nk == 0 && n > 0) {        // never empty
+        if (nk == 0 && have_fallback) {        // never empty (among the hypotheses the mask test left)
             keep_idx[0] = (int)(s_min & 0xffffffffull);
             nk = 1;
         }
@@ -636,7 +651,8 @@ extern "C" int zs_features_multi(zs_ctx* ctx, int n_seg, const int32_t* obj_slot
     return ZS_OK;
 }
 
-extern "C" int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, int32_t* viol_out, void* stream) {
+extern "C" int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, const uint8_t* mask, double mask_th,
+                             int32_t* viol_out, void* stream) {
     obj_view o;
     zs_cam cam;
     if (ctx && n == 0) return ZS_OK;
@@ -644,17 +660,83 @@ extern "C" int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int 
     if (rc) return rc;
     if (n < 0 || !viol_out) return zs_fail(ctx, ZS_ERR_INVALID, "n %d", n);
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    // smallest in-mask count c that the reference keeps: c / N > th in float64 (zephyr_utils.py:68-70)
+    int mask_min = 0;
+    if (mask) {
+        mask_min = (int)floor((double)mask_th * (double)o.n_pts) - 1;
+        if (mask_min < 0) mask_min = 0;
+        while (mask_min <= o.n_pts && !((double)mask_min / (double)o.n_pts > (double)mask_th)) ++mask_min;
+    }
     const bool in_smem = cloud_smem(o.n_pts) <= kCloudSmemMax;
     const cta_shape cs = shape_for(in_smem ? cloud_smem(o.n_pts) : 0, 0);
     const int grid = grid_for(ctx, n, cs.ctas_per_sm, cs.threads / 32);
     cudaStream_t st = (cudaStream_t)stream;
-    if (in_smem) {
-        rc = opt_in_smem(ctx, zs_k_violations<true>, cs.smem);
-        if (rc) return rc;
-        zs_k_violations<true><<<grid, cs.threads, cs.smem, st>>>(o, cam, ctx->frame.packed, poses, n, viol_out);
-    } else {
-        zs_k_violations<false><<<grid, cs.threads, 0, st>>>(o, cam, ctx->frame.packed, poses, n, viol_out);
+#define ZS_LAUNCH_VIOL(SM, MK)                                                                                       \
+    do {                                                                                                             \
+        if (SM) { rc = opt_in_smem(ctx, zs_k_violations<SM, MK>, cs.smem); if (rc) return rc; }                      \
+        zs_k_violations<SM, MK><<<grid, cs.threads, SM ? cs.smem : 0, st>>>(o, cam, ctx->frame.packed, poses, n,     \
+                                                                           mask, mask_min, viol_out);                \
+    } while (0)
+    if (in_smem) { if (mask) ZS_LAUNCH_VIOL(true, true); else ZS_LAUNCH_VIOL(true, false); }
+    else         { if (mask) ZS_LAUNCH_VIOL(false, true); else ZS_LAUNCH_VIOL(false, false); }
+#undef ZS_LAUNCH_VIOL
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
+// DTOID detections -> binary mask (python/ossid/scripts/online_learning.py:389-405): boxes are visited in order; a box
+// with score < 0.5 is skipped once the mask already covers a pixel with depth; every other box is grown by
+// expandBox (python/ossid/utils/__init__.py:11-16) and filled.  "The mask covers a pixel with depth" only changes when a
+// box is filled, so the single CTA carries it as a flag and tests just the pixels of the box it has filled.
+namespace {
+constexpr int kMaxBoxes = 64;
+struct box_list { int n; int x1[kMaxBoxes], y1[kMaxBoxes], x2[kMaxBoxes], y2[kMaxBoxes]; int low_score[kMaxBoxes]; };
+
+__global__ void __launch_bounds__(1024)
+zs_k_boxes_to_mask(const __grid_constant__ box_list bl, const float4* __restrict__ frame, int H, int W, uint8_t* __restrict__ mask) {
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) mask[i] = 0;
+    __syncthreads();
+    for (int b = 0; b < bl.n; ++b) {
+        if (bl.low_score[b] && s_any) continue;                        // block-uniform (s_any only changes behind a barrier)
+        const int bw = bl.x2[b] - bl.x1[b], bh = bl.y2[b] - bl.y1[b];
+        int any = 0;
+        if (bw > 0 && bh > 0) {
+            for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
+                const int px = (bl.y1[b] + i / bw) * W + bl.x1[b] + i % bw;
+                mask[px] = 1;
+                any |= frame[px].x > 0.f;                              // .x = depth / camera_scale
+            }
+        }
+        __syncthreads();
+        if (any) atomicOr(&s_any, 1);
+        __syncthreads();
     }
+}
+}  // namespace
+
+extern "C" int zs_boxes_to_mask(zs_ctx* ctx, const double* boxes, const double* scores, int n_boxes, double expand_ratio,
+                                uint8_t* mask_out, void* stream) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (!ctx->frame.set) return zs_fail(ctx, ZS_ERR_STATE, "frame not set");
+    if (n_boxes < 0 || n_boxes > kMaxBoxes || !mask_out || (n_boxes > 0 && (!boxes || !scores)))
+        return zs_fail(ctx, ZS_ERR_INVALID, "zs_boxes_to_mask: %d boxes (at most %d)", n_boxes, kMaxBoxes);
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int H = ctx->frame.H, W = ctx->frame.W;
+    box_list bl;
+    bl.n = n_boxes;
+    for (int i = 0; i < n_boxes; ++i) {
+        // expandBox, float64 as in Python; int() truncates toward zero; numpy slicing clips to the array
+        const double x1 = boxes[4 * i], y1 = boxes[4 * i + 1], x2 = boxes[4 * i + 2], y2 = boxes[4 * i + 3];
+        const double cx = (x1 + x2) / 2, cy = (y1 + y2) / 2, w = x2 - x1, h = y2 - y1;
+        const double ex1 = fmax(0.0, cx - w / 2 * expand_ratio), ex2 = fmin((double)(W - 1), cx + w / 2 * expand_ratio);
+        const double ey1 = fmax(0.0, cy - h / 2 * expand_ratio), ey2 = fmin((double)(H - 1), cy + h / 2 * expand_ratio);
+        auto clip = [](double v, int hi) { long long t = (long long)v; if (t < 0) t += hi; return (int)(t < 0 ? 0 : (t > hi ? hi : t)); };
+        bl.x1[i] = clip(ex1, W); bl.x2[i] = clip(ex2, W); bl.y1[i] = clip(ey1, H); bl.y2[i] = clip(ey2, H);
+        bl.low_score[i] = scores[i] < 0.5;
+    }
+    zs_k_boxes_to_mask<<<1, 1024, 0, (cudaStream_t)stream>>>(bl, ctx->frame.packed, H, W, mask_out);
     ZS_LAUNCHED(ctx);
     return ZS_OK;
 }

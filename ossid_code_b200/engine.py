@@ -203,12 +203,31 @@ class ZsContext:
                  "zs_mask_count")
         return cnt
 
-    def violations(self, slot: int, poses12, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def violations(self, slot: int, poses12, out: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+                   mask_th: float = 0.5) -> torch.Tensor:
+        """Free-space violation count per hypothesis; with ``mask`` (device uint8 (H,W)) the mask-overlap test of
+        ``filterHypoByMask`` runs in the same pass and failing hypotheses report ``ZS_VIOL_MASKED``."""
         n = poses12.shape[0]
         viol = out if out is not None else torch.empty((n,), dtype=torch.int32, device=self.device)
-        self._ck(self.lib.zs_violations(self.h, slot, poses12.data_ptr(), n, viol.data_ptr(), self._stream()),
-                 "zs_violations")
+        if mask is not None and (not mask.is_cuda or mask.dtype != torch.uint8 or tuple(mask.shape) != tuple(self.frame_hw)
+                                 or not mask.is_contiguous()):
+            raise ValueError("mask must be a contiguous uint8 CUDA tensor of the frame's shape")
+        self._ck(self.lib.zs_violations(self.h, slot, poses12.data_ptr(), n, mask.data_ptr() if mask is not None else None,
+                                        float(mask_th), viol.data_ptr(), self._stream()), "zs_violations")
         return viol
+
+    def boxes_to_mask(self, boxes, scores, expand_ratio: float = 1.2, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """DTOID boxes (n,4) x1 y1 x2 y2 + scores (n,) -> uint8 (H,W) mask on the device (online_learning.py:389-405),
+        against the resident frame's depth."""
+        b = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 4))
+        sc = np.ascontiguousarray(np.asarray(scores, dtype=np.float64).reshape(-1))
+        if len(b) != len(sc):
+            raise ValueError("boxes and scores differ in length")
+        H, W = self.frame_hw
+        mask = out if out is not None else torch.empty((H, W), dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.zs_boxes_to_mask(self.h, b.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), len(b),
+                                           float(expand_ratio), mask.data_ptr(), self._stream()), "zs_boxes_to_mask")
+        return mask
 
     def filter(self, viol, n_pts: int, th: float) -> torch.Tensor:
         """Kept hypothesis indices (ascending, int32).  Reads the count back: one 4-byte sync."""

@@ -171,7 +171,7 @@ class FrameScorer:
     def __init__(self, weights: Sequence[dict], device: Optional[int] = None, precision: str = "bf16",
                  inconst_ratio_th: float = 100.0, k: int = 8, chunk: int = 32768, group=None,
                  ctx: Optional[ZsContext] = None, reorder_points: bool = True, rerank: Optional[bool] = None,
-                 fused: bool = True):
+                 fused: bool = True, mask_th: float = 0.5):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         if len(weights) > MAX_WEIGHT_SLOTS:
@@ -182,6 +182,7 @@ class FrameScorer:
         self.precision = precision
         self.split = precision == "fp32"      # fp32-accurate: split-bf16 features + the 3-term tcgen05 scorer + the fp32 head
         self.th, self.k, self.chunk, self.group = float(inconst_ratio_th), int(k), int(chunk), group
+        self.mask_th = float(mask_th)     # filterHypoByMask's th for objects that come with a detection mask / boxes
         self.rerank = (precision == "bf16") if rerank is None else bool(rerank and precision == "bf16")
         # bf16 path without pre-filter: features are computed inside the MLP kernel (zs_pool_fused) instead of being
         # written to HBM by zs_features and read back; fused=False keeps the two-kernel sequence (bit-identical results)
@@ -199,6 +200,7 @@ class FrameScorer:
         self._plans = {}
         self._copy_stream = None
         self._img_dev = self._depth_dev = None
+        self._mask_dev, self._masks = None, []
         self._raw = [None, None]          # staging of the raw (m,4,4) pose blocks, double-buffered
         self._raw_free = [None, None]     # event: the pack kernel that last read _raw[b] has run
         self._p12 = [None, None]
@@ -255,9 +257,9 @@ class FrameScorer:
         return 0, 1
 
     # -- per-shape plan -----------------------------------------------------------------
-    def _make_plan(self, counts, wslots, npts):
+    def _make_plan(self, counts, wslots, npts, masked=False):
         rank, world = self._rank_world()
-        key = (tuple(counts), tuple(wslots), tuple(npts), rank, world, self.k)
+        key = (tuple(counts), tuple(wslots), tuple(npts), rank, world, self.k, bool(masked))
         plan = self._plans.get(key)
         if plan is not None:
             return plan
@@ -285,7 +287,8 @@ class FrameScorer:
         plan.rec_ints = record_ints(n_obj, k, self.rerank)
         plan.pose_at = record_pose_offset(n_obj, k)
         plan.rec = torch.zeros((plan.rec_ints,), dtype=torch.int32, device=dev)
-        if self.th >= 100:         # no pre-filter: every rank "kept" its hypotheses; with one, zs_filter writes this section
+        plan.filtered = self.th < 100 or bool(masked)
+        if not plan.filtered:      # no pre-filter: every rank "kept" its hypotheses; with one, zs_filter writes this section
             plan.rec[2 * n_obj * k: 2 * n_obj * k + 2 * n_obj] = torch.tensor([[1, 0]] * n_obj, dtype=torch.int32).reshape(-1).to(dev)
         else:                      # device-side pre-filter state: violation counts, kept lists (= the top-k index map) and
             plan.viol = torch.zeros((max(total, 1),), dtype=torch.int32, device=dev)     # counts (= the segment table)
@@ -356,7 +359,8 @@ class FrameScorer:
         counts = [len(ob["pose_hypos"]) for ob in objects]
         wslots = [weight_of(o) % max(self.n_weights, 1) for o in range(len(objects))]
         npts = [len(ob["model_points"]) for ob in objects]
-        return self._make_plan(counts, wslots, npts)
+        masked = any(("mask" in ob) or ("boxes" in ob) for ob in objects)
+        return self._make_plan(counts, wslots, npts, masked)
 
     def upload(self, img_u8, depth, cam_K, objects: List[dict], weight_of=lambda o: 0, prefetched=None):
         """Copy one frame's inputs to the device and keep them resident; this rank's pose slices only."""
@@ -383,9 +387,21 @@ class FrameScorer:
             plan = self._plan_for(objects, weight_of)
             buf = self._buf ^ 1
             ev = self._stage_poses(objects, plan, buf, stream)
+        self._masks = [None] * len(objects)
         for o, ob in enumerate(objects):
             pts, cols, nrms = host = self._host_cloud(ob)
             ctx.set_object(o, pts, cols, nrms, token=host)      # skipped when this slot already holds this cloud
+            # detection prior of the object (the reference's DTOID stage, online_learning.py:383-405): a mask, or boxes
+            # that are rasterised on the device against this frame's depth; applied as filterHypoByMask in the pre-filter
+            if "mask" in ob or "boxes" in ob:
+                if self._mask_dev is None or self._mask_dev.shape[0] < len(objects) or self._mask_dev.shape[1:] != tuple(ctx.frame_hw):
+                    self._mask_dev = torch.zeros((len(objects),) + tuple(ctx.frame_hw), dtype=torch.uint8, device=ctx.device)
+                m = self._mask_dev[o]
+                if "mask" in ob:
+                    m.copy_((torch.as_tensor(ob["mask"]) != 0).to(torch.uint8), non_blocking=True)
+                else:
+                    ctx.boxes_to_mask(ob["boxes"], ob["box_scores"], ob.get("box_expand", 1.2), out=m)
+                self._masks[o] = m
         # one cast kernel over the whole concatenated block: (total,4,4) f32/f64 -> (total,12) f32
         stream.wait_event(ev)
         p12 = self._p12[buf]
@@ -419,13 +435,13 @@ class FrameScorer:
         #    zs_set_dynamic_count) and buffers are laid out by capacity, so a filtered frame is as asynchronous as an
         #    unfiltered one.
         keeps, n_keeps, n_devs = [], [], []
-        filtered = self.th < 100
+        filtered = plan.filtered
         for o, r in enumerate(res):
             keep, n_dev, M = None, None, r["poses12"].shape[0]
             if filtered and M > 0:
                 # the kept list lands in the top-k index map and the kept count in the segment table: no glue kernels
                 a = plan.off[o]
-                viol = ctx.violations(r["slot"], r["poses12"], out=plan.viol[a: a + M])
+                viol = ctx.violations(r["slot"], r["poses12"], out=plan.viol[a: a + M], mask=self._masks[o], mask_th=self.mask_th)
                 keep, n_dev = ctx.filter_async(viol, ctx.obj_npts[r["slot"]], self.th, info=info[2 * o: 2 * o + 2],
                                                keep_out=plan.index_map[a: a + M],
                                                n_keep_out=plan.seg_dyn.view(-1)[4 * o + 1: 4 * o + 2])

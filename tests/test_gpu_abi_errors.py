@@ -19,7 +19,7 @@ def test_status_codes_and_messages():
     # unset slots
     assert lib.zs_score(h, 3, x.data_ptr(), 0, 4, 16, 0, out.data_ptr(), st) == -3           # ZS_ERR_STATE
     assert b"weight slot 3" in lib.zs_last_error(h)
-    assert lib.zs_violations(h, 63, x.data_ptr(), 1, out.data_ptr(), st) == -3
+    assert lib.zs_violations(h, 63, x.data_ptr(), 1, None, 0.5, out.data_ptr(), st) == -3
     # bad arguments
     ctx.set_weights(0, weights.seeded_folded(0))
     assert lib.zs_score(h, 0, x.data_ptr(), 0, 4, 16, 1, out.data_ptr(), st) == -4           # precision / dtype mismatch

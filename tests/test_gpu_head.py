@@ -403,6 +403,46 @@ def test_frame_scorer_fused_equals_unfused(ctx):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_frame_scorer_with_detection_boxes_equals_oracle_pipeline(ctx, precision):
+    """LM-O-style frame (BASELINE.json configs[2]): every object comes with DTOID boxes; the boxes are rasterised on the
+    device, the mask-overlap test runs inside the pre-filter pass, and the scored set / top-1 equal the oracle pipeline
+    boxes_to_mask -> filterHypoByMask -> features -> scorer -> argmax; also sharded over 3 emulated ranks."""
+    import cv2
+    sc = syn.make_scene(61, "lmo", n_obj=3, n_pts=256, n_hypo=300)
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    wof = lambda o: o % 2
+    meta = glue.K2meta(sc["cam_K"])
+    img01 = cv2.GaussianBlur(sc["img"], (5, 5), 0) / 255.
+    for o, ob in enumerate(sc["objects"]):
+        x1, y1, x2, y2 = syn.gt_box(sc, ob, 1.0)
+        ob["boxes"] = np.array([[x1, y1, x2, y2], [5.0, 5.0, 40.0, 40.0]], dtype=np.float64)
+        ob["box_scores"] = np.array([0.8, 0.3])
+    sc["objects"][2]["boxes"] = np.array([[600.0, 440.0, 630.0, 470.0]])            # a box no hypothesis projects into
+    sc["objects"][2]["box_scores"] = np.array([0.9])
+    fs = scoring.FrameScorer(ws, device=0, precision=precision, inconst_ratio_th=100.0, k=8)
+    S, I = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=wof)
+    n_scored = 0
+    for o, ob in enumerate(sc["objects"]):
+        mask = zo.boxes_to_mask(sc["depth"], ob["boxes"], ob["box_scores"])
+        kept = zo.mask_filter(zo.project_raw(ob["pose_hypos"], ob["model_points"], meta), torch.from_numpy(mask.astype(np.int64)),
+                              256, th=0.5).numpy()
+        idx = np.nonzero(kept)[0]
+        n_scored += len(idx)
+        got = [int(i) for i in I[o] if i >= 0]
+        assert set(got) <= set(idx.tolist()), f"object {o}: a hypothesis outside the detection mask was scored"
+        if len(idx) == 0:
+            assert got == []
+            continue
+        f = zo.features(img01, sc["depth"], ob["pose_hypos"][idx], meta, ob["model_points"], ob["model_colors"], ob["model_normals"])
+        ref = zo.scorer(f["point_x"], ws[o % 2])
+        assert got[0] == int(idx[int(torch.argmax(ref))]), f"object {o}: top-1 differs from the oracle pipeline"
+        assert abs(float(S[o, 0]) - float(ref.max())) <= 1e-4 * float(ref.abs().max()) + 1e-6
+    assert fs.last_scored == n_scored and (I[2] < 0).all() and 0 < n_scored < 900
+    Sm, Im, _ = _emulate_ranks(fs, sc, 3, wof)
+    assert np.array_equal(Im, I) and np.array_equal(Sm, S)
+
+
 def test_more_objects_than_cloud_slots_raises(ctx):
     sc = syn.make_scene(19, "tiny", n_obj=1, n_pts=32, n_hypo=4)
     fs = scoring.FrameScorer([weights.seeded_folded(0)], device=0, k=2)

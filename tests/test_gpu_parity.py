@@ -145,6 +145,42 @@ def test_project_uv_and_mask_filter_match_golden(ctx, golden_dir):
         assert np.array_equal(kept, g[key]), f"filterHypoByMask th={th}"
 
 
+def test_boxes_to_mask_matches_reference_fixture(ctx, golden_dir):
+    """Device-side DTOID box -> mask rasterisation == the reference's own statements (fixture boxes_mask.npz)."""
+    g = np.load(os.path.join(golden_dir, "boxes_mask.npz"))
+    H, W = g["depth"].shape
+    ctx.set_frame_u8(np.zeros((H, W, 3), np.uint8), g["depth"], glue.K2meta(syn.cam_K("tiny")))
+    for tag in "abc":
+        m = ctx.boxes_to_mask(g[f"{tag}_boxes"], g[f"{tag}_scores"]).cpu().numpy()
+        assert np.array_equal(m, g[f"{tag}_mask"]), tag
+    assert int(ctx.boxes_to_mask(np.zeros((0, 4)), np.zeros((0,))).sum()) == 0
+
+
+@pytest.mark.parametrize("th", [0.5, 0.9, 0.0])
+def test_mask_early_out_in_the_prefilter_matches_reference_filter(ctx, golden_dir, th):
+    """zs_violations with a mask: hypotheses the reference's filterHypoByMask rejects (fixture mask_filter.npz) report
+    ZS_VIOL_MASKED and never reach the kept list; the others carry their ordinary violation count."""
+    g = np.load(os.path.join(golden_dir, "mask_filter.npz"))
+    H, W = g["mask"].shape
+    rng = np.random.default_rng(0)
+    depth = rng.uniform(0.3, 1.2, (H, W)).astype(np.float32)
+    meta = glue.K2meta(g["cam_K"])
+    ctx.set_frame_u8(np.zeros((H, W, 3), np.uint8), depth, meta)
+    n = len(g["model_points"])
+    ctx.set_object(0, g["model_points"], np.full((n, 3), 0.5), np.tile([0.0, 0.0, 1.0], (n, 1)))
+    p12 = poses_to_rt12(g["pose_hypos"], ctx.device)
+    mask = torch.from_numpy(g["mask"]).to(ctx.device)
+    plain = ctx.violations(0, p12)
+    masked = ctx.violations(0, p12, mask=mask, mask_th=th)
+    kept_ref = torch.from_numpy(g[f"kept_{int(th * 100):03d}"].astype(bool)).to(ctx.device)
+    assert torch.equal(masked != 0x7fffffff, kept_ref), "mask test differs from the reference's filterHypoByMask"
+    assert torch.equal(masked[kept_ref], plain[kept_ref])
+    keep = ctx.filter(masked, n, 100.0)
+    assert torch.equal(keep.long(), torch.nonzero(kept_ref).reshape(-1))
+    all_rejected = torch.full_like(masked, 0x7fffffff)
+    assert ctx.filter(all_rejected, n, 10.0).numel() == 0, "nothing survives the mask test: the kept list is empty"
+
+
 def test_projection_matches_reference_fixture(ctx, golden_dir):
     """GPU uv / front-facing selection vs the reference's projectModelPoint output (fixture)."""
     g = np.load(os.path.join(golden_dir, "projection.npz"))

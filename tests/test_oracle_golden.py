@@ -80,6 +80,16 @@ def test_glue_mirror_matches_reference_networkInference(golden_dir, tag, th):
         assert len(scores) < len(g["pose_hypos"])           # the pre-filter really dropped something
 
 
+def test_boxes_to_mask_matches_the_reference_statements(golden_dir):
+    """oracle.boxes_to_mask vs the mask produced by the reference's own box -> mask statements
+    (python/ossid/scripts/online_learning.py:389-405, AST-extracted and executed by oracle/gen_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "boxes_mask.npz"))
+    for tag in "abc":
+        m = zo.boxes_to_mask(g["depth"], g[f"{tag}_boxes"], g[f"{tag}_scores"])
+        assert np.array_equal(m.astype(np.uint8), g[f"{tag}_mask"]), tag
+    assert g["a_mask"].sum() > 0 and not np.array_equal(g["a_mask"], g["b_mask"])
+
+
 def test_rgb_to_hsv_matches_colorsys():
     rng = np.random.default_rng(0)
     rgb = np.concatenate([rng.uniform(0, 1, (500, 3)), [[0, 0, 0], [1, 1, 1], [.5, .5, .5], [1, 0, 0], [0, 1, 0],
