@@ -41,6 +41,9 @@ WORKLOADS = {
     "c1": ("lmo", 1, 1000, 1000, "synthetic 640x480, 1 object x 1,000 hypotheses x 1,000 pts"),
     "c2": ("ycbv", 21, 10000, 1000, "YCB-V-shaped frame: 21 objects x 10,000 hypotheses x 1,000 pts"),
     "c3": ("lmo", 8, 50000, 1000, "LM-O-shaped frame: 8 objects x 50,000 hypotheses x 1,000 pts, all inside DTOID-style box crops"),
+    # the same frame BEFORE the detector's crop is applied: the hypothesis mixture is unfiltered, every object carries its
+    # DTOID-style box, and box -> mask rasterisation + the mask-overlap pre-filter run inside the timed step
+    "c3f": ("lmo", 8, 50000, 1000, "LM-O-shaped frame: 8 objects x 50,000 unfiltered hypotheses + DTOID-style boxes; box->mask and mask pre-filter inside the step"),
     "c4": ("hd", 1, 200000, 4000, "bandwidth stress: 1280x720, 1 object x 200,000 hypotheses x 4,000 pts"),
     # a step = the 32 frames scored between two finetune rounds (online_learning.py: finetune_interval); frames are C2-shaped
     "c5": ("ycbv", 21, 10000, 1000, "online-learning stream: 32 frames x (21 objects x 10,000 hypotheses x 1,000 pts) per step"),
@@ -73,6 +76,9 @@ def make_workload(name, n_gpus, seed=1, gpu=True):
             extra = [syn.make_hypotheses(rng, ob["gt_pose"], min(per_gpu, 10000), sc["cam_K"], sc["H"], sc["W"])
                      for _ in range(reps - 1)]
             ob["pose_hypos"] = np.concatenate([ob["pose_hypos"], *extra])[: per_gpu * n_gpus]
+        if name == "c3f":    # detector output for this object: its box (before expandBox) and a confident score
+            ob["boxes"] = np.asarray([syn.gt_box(sc, ob, 1.0)], dtype=np.float64)
+            ob["box_scores"] = np.asarray([0.9])
     return sc
 
 
@@ -216,7 +222,7 @@ def config_for(args, world, scaling):
             "frames_per_step": n_frames, "objects": n_obj, "points_per_object": n_pts, "topk": args.k,
             "inconst_ratio_th": args.inconst_th,
             "kernels": ("fused projection+gather+features+MLP+max-pool kernel" if (args.precision == "bf16" and not args.no_fuse
-                        and args.inconst_th >= 100) else "zs_features -> zs_pool (features through HBM)"),
+                        and args.inconst_th >= 100 and args.workload != "c3f") else "zs_features -> zs_pool (features through HBM)"),
             "parallelism": (f"hypothesis-sharded x{world}, one all-gather of top-k records" if world > 1 else "single GPU"),
             "l2": "feature chunks of 32768 hypotheses x 1000 pts (>= 0.5 GB) exceed the 126 MB L2; no flush needed",
             "weights": "seeded random (no checkpoint is published)"}
@@ -308,7 +314,8 @@ class Runner:
             pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
             objs = [dict(model_points=pin(ob["model_points"]), model_colors=pin(ob["model_colors"]),
                          model_normals=pin(ob["model_normals"]),
-                         pose_hypos=pin(ob["pose_hypos"].astype(np.float32))) for ob in sc["objects"]]
+                         pose_hypos=pin(ob["pose_hypos"].astype(np.float32)),
+                         **{k: ob[k] for k in ("boxes", "box_scores") if k in ob}) for ob in sc["objects"]]
             self.frame = dict(img=pin(sc["img"]), depth=pin(sc["depth"]), cam_K=sc["cam_K"], objects=objs)
         return self.frame
 
@@ -404,7 +411,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = total_hyp / (ms_step * 1e-3)
-    scored = int(fs.last_scored) * n_frames if args.inconst_th < 100 else total_hyp
+    scored = int(fs.last_scored) * n_frames if fs._plan.filtered else total_hyp
 
     # ---- end-to-end arm through the public host-buffer API: `e2e` ----------------------------------
     # per frame: H2D of the uint8 image, the float32 depth and this rank's pose hypotheses, D2H of the top-k; the model

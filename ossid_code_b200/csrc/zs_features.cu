@@ -1,15 +1,25 @@
-// Kernel 1 family: projection, gather, per-point residual features, masks, violation counts,
-// hypothesis pre-filter, raw uv projection, mask-overlap count.  ABI: include/zs.h.
+// Kernel 1 family: projection, gather, per-point residual features, masks, violation counts, hypothesis pre-filter
+// (free-space test + detection-mask overlap), DTOID box -> mask rasterisation, raw uv projection, mask-overlap count.
+// ABI: include/zs.h.
 //
-// Mapping (all kernels here): one WARP owns one hypothesis at a time; lanes stride over the
-// model points, so every per-point store is a contiguous, fully coalesced warp store
-// (features: 32 lanes x 32 B fp32 or 16 B bf16; mask: 32 x 1 B; uv: 32 x 8 B).  The pose sits in
-// registers, the model cloud (36 B/point) in shared memory, the packed frame (16 B/pixel, a few
-// MB) is gathered through the read-only path and lives in L1/L2.  Grids are a multiple of the
-// SM count; warps walk the hypothesis list with a grid stride.
+// Three feature kernels share the per-point code of zs_common.cuh (zs_feat_phase1 / zs_feat_phase2):
+//   zs_k_features_hot / zs_k_features_multi   features only.  Work unit = a 256-point chunk of a hypothesis, owned by
+//       one warp; every lane carries two points per iteration (two frame gathers in flight); branch-free body; rows
+//       leave as one 16-byte (bf16), 32-byte (fp32, st.global.v8) or 2 x 16-byte (split bf16) store per lane, the warp
+//       writing contiguous memory.  _multi walks several objects (segments) in one launch.
+//   zs_k_features<.., kAux = true>            features + uv / mask / violation-count side outputs.  A warp owns a whole
+//       hypothesis (its violation count is a warp-local sum); fp32 rows are transposed through a per-warp shared-memory
+//       staging buffer so that the stores are contiguous.
+//   the producer warps of zs_k_mlp_tc<true>   (zs_score_tc.cu) featurise the tile the tensor cores are about to read:
+//       the headline path, no feature rows in HBM at all.
+// In all of them the pose sits in registers, the model cloud (36 B/point) in shared memory (global / L2 in the fused
+// kernel, whose shared memory holds the weights), and the packed frame (16 B/pixel, a few MB, L2-resident) is gathered
+// through the read-only path.  One 32-warp CTA per SM; warps walk their units with a grid stride.
 //
-// Everything that decides an integer or a mask bit uses the non-contractable intrinsics of
-// zs_common.cuh in the oracle's order; the remaining float features may use FMA / MUFU.
+// Everything that decides an integer or a mask bit uses the non-contractable intrinsics of zs_common.cuh in the
+// oracle's order; the remaining float features may use FMA / MUFU.
+#include <stdlib.h>
+
 #include "zs_common.cuh"
 
 namespace {
@@ -41,9 +51,9 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 
-// fp32 features: a lane holds 32 contiguous bytes of its point, so a direct store would write two
-// half-filled 32-byte sectors per lane.  Stage the warp's 32 x 32 B through shared memory and write
-// two fully contiguous 512-byte warp stores instead.  `n_act` = points of this warp-iteration.
+// Side-output kernel (zs_k_features<.., true>) only: a lane holds the 32 contiguous bytes of its point's fp32 row; the
+// warp's 32 x 32 B go through shared memory and leave as two fully contiguous 512-byte warp stores.  (The hot kernels
+// write the row with one 256-bit store per lane instead, see st_f32_row.)  `n_act` = points of this warp-iteration.
 __device__ __forceinline__ void store_f32_rows(float4* __restrict__ wbuf, int lane, float4* __restrict__ dst, int n_act,
                                                float4 lo, float4 hi) {
     wbuf[lane * 2] = lo;
@@ -220,12 +230,49 @@ __device__ __forceinline__ void st_f32_row(float* p, float4 lo, float4 hi, bool 
 
 // kFmt: ZS_F32 (32-byte rows), ZS_BF16 (16-byte rows) or ZS_BF16_SPLIT (per hypothesis a plane of bf16(x) rows followed by
 // a plane of bf16(x - bf16(x)) rows: the two K halves of the fp32-accurate scorer's layer-1 operand, zs_score_tc3.cu).
+// ---- experiment variant, build with -DZS_CROP_STAGE (tools/README.md): the crop of the packed frame named by the
+// environment variable ZS_CROP_RECT="x0,y0,w,h" is staged into shared memory next to the model cloud by the TMA unit
+// (one cp.async.bulk per crop row, completion on an mbarrier), and gathers that fall inside it read shared memory;
+// the others keep the read-only global path.  This is the "RGB-D crop resident in shared memory" layout that
+// BASELINE.json's north_star describes; measured slower than the L2 path, hence not the default.
+struct crop_view { const float4* s; int x0, y0, w, h; };
+#ifdef ZS_CROP_STAGE
+__device__ __forceinline__ float4 gather_px(const float4* __restrict__ frame, const zs_cam& cam, const crop_view& cv, int pix) {
+    const int v = pix / cam.W, u = pix - v * cam.W;
+    const unsigned du = (unsigned)(u - cv.x0), dv = (unsigned)(v - cv.y0);
+    if (du < (unsigned)cv.w && dv < (unsigned)cv.h) return cv.s[dv * cv.w + du];
+    return __ldg(frame + pix);
+}
+__device__ __forceinline__ void stage_crop(const float4* __restrict__ frame, const zs_cam& cam, crop_view& cv, char* smem_crop) {
+    __shared__ __align__(8) unsigned long long crop_bar;
+    cv.s = reinterpret_cast<const float4*>(smem_crop);
+    if (cv.w <= 0 || cv.h <= 0) return;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&crop_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(cv.w * cv.h * 16)) : "memory");
+    __syncthreads();
+    for (int r = threadIdx.x; r < cv.h; r += blockDim.x) {          // one bulk copy (TMA unit) per crop row
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_crop + (size_t)r * cv.w * 16);
+        const float4* src = frame + (size_t)(cv.y0 + r) * cam.W + cv.x0;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"((uint32_t)(cv.w * 16)), "r"(bar) : "memory");
+    }
+    asm volatile("{\n\t.reg .pred p;\n\tWAITC_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra DONEC_%=;\n\tbra WAITC_%=;\n\tDONEC_%=:\n\t}"
+                 ::"r"(bar) : "memory");
+}
+#endif
+
 // The units of ONE object that this warp owns: first_unit, first_unit + n_warps, ...
 template <int kFmt, bool kSmem>
 __device__ __forceinline__ void hot_units(const obj_view& o, const zs_cam& cam, const float4* __restrict__ frame,
                                           const float* __restrict__ poses, const int32_t* __restrict__ keep_idx, int n_keep,
                                           void* __restrict__ feat_out, int aligned32, const float4* sA, const float4* sB,
-                                          const float* sV, long long first_unit, int n_warps) {
+                                          const float* sV, long long first_unit, int n_warps, const crop_view cv = crop_view{}) {
     constexpr int kIlp = 2, kChunk = 256;
     const int lane = threadIdx.x & 31;
     const int N = o.n_pts;
@@ -249,7 +296,11 @@ __device__ __forceinline__ void hot_units(const obj_view& o, const zs_cam& cam, 
                 q[j] = min(p0 + j * 32 + lane, p_end - 1);
                 a[j] = kSmem ? sA[q[j]] : __ldg(sA + q[j]);
                 zs_feat_phase1(T, cam, a[j], x[j], y[j], z[j], uf[j], vf[j], valid[j], pix);
+#ifdef ZS_CROP_STAGE
+                px[j] = gather_px(frame, cam, cv, pix);
+#else
                 px[j] = __ldg(frame + pix);                  // {d_obs, H, S, V}; pixel 0 when invalid
+#endif
             }
 #pragma unroll
             for (int j = 0; j < kIlp; ++j) {                 // phase 2: residual features, store
@@ -285,15 +336,18 @@ template <int kFmt, bool kSmem>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 zs_k_features_hot(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
                   const int32_t* __restrict__ keep_idx, int n_keep, void* __restrict__ feat_out, int aligned32,
-                  const int32_t* __restrict__ n_dev, int n_off) {
+                  const int32_t* __restrict__ n_dev, int n_off, crop_view cv) {
     n_keep = zs_dyn_count(n_dev, n_off, n_keep);
     extern __shared__ __align__(16) char smem[];
     float4 *sA, *sB;
     float* sV;
     stage_cloud<kSmem>(o, sA, sB, sV, smem);
+#ifdef ZS_CROP_STAGE
+    stage_crop(frame, cam, cv, smem + (kSmem ? cloud_smem(o.n_pts) : 0));
+#endif
     const int warps_per_cta = blockDim.x >> 5;
     hot_units<kFmt, kSmem>(o, cam, frame, poses, keep_idx, n_keep, feat_out, aligned32, sA, sB, sV,
-                           blockIdx.x * warps_per_cta + (threadIdx.x >> 5), gridDim.x * warps_per_cta);
+                           blockIdx.x * warps_per_cta + (threadIdx.x >> 5), gridDim.x * warps_per_cta, cv);
 }
 
 // Several objects in one launch (a frame's objects share the frame but not the model cloud): every CTA walks the
@@ -562,7 +616,16 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
     const bool in_smem = cloud_smem(o.n_pts) <= kCloudSmemMax;
     const bool aux = uv_out || mask_out || viol_out;
     const cta_shape cs = shape_for(in_smem ? cloud_smem(o.n_pts) : 0, (aux && feat_dtype == ZS_F32) ? 1024 : 0);   // fp32 store staging (side-output kernel): 1 KB/warp
-    const size_t smem = cs.smem;
+    size_t smem = cs.smem;
+    crop_view cv{nullptr, 0, 0, 0, 0};
+#ifdef ZS_CROP_STAGE
+    if (const char* e = aux ? nullptr : getenv("ZS_CROP_RECT")) {      // the hot (features-only) kernels only
+        if (sscanf(e, "%d,%d,%d,%d", &cv.x0, &cv.y0, &cv.w, &cv.h) != 4 || cv.x0 < 0 || cv.y0 < 0 || cv.w <= 0 || cv.h <= 0 ||
+            cv.x0 + cv.w > cam.W || cv.y0 + cv.h > cam.H || smem + (size_t)cv.w * cv.h * 16 > 220 * 1024)
+            return zs_fail(ctx, ZS_ERR_INVALID, "ZS_CROP_RECT=%s does not fit the frame / %zu bytes of shared memory", e, (size_t)220 * 1024 - smem);
+        smem += (size_t)cv.w * cv.h * 16;
+    }
+#endif
     const int threads = cs.threads;
     const long long units = aux ? n_keep : (long long)n_keep * ((o.n_pts + 255) / 256);
     const int grid = grid_for(ctx, units, cs.ctas_per_sm, threads / 32);
@@ -582,7 +645,7 @@ extern "C" int zs_features(zs_ctx* ctx, int obj_slot, const float* poses, const 
             zs_k_features_hot<FMT, SM><<<grid, threads, smem, st>>>(o, cam, frame, poses,               \
                                                                    keep_idx, n_keep, feat_out,          \
                                                                    (((uintptr_t)feat_out & 31) == 0),   \
-                                                                   ctx->dyn_n, ctx->dyn_off);           \
+                                                                   ctx->dyn_n, ctx->dyn_off, cv);       \
         }                                                                                               \
     } while (0)
     if (feat_dtype == ZS_BF16) { if (in_smem) ZS_LAUNCH_FEAT(ZS_BF16, true); else ZS_LAUNCH_FEAT(ZS_BF16, false); }

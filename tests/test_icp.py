@@ -97,7 +97,7 @@ def test_kernel_icp_matches_oracle(n_pts, n_pose):
         assert abs(st[h, 0] - info["fitness"]) <= 2.0 / n_pts + 1e-6, (h, st[h], info)
         assert abs(st[h, 1] - info["inlier_rmse"]) <= 2e-5, (h, st[h], info)
     print(f"n_pts={n_pts}: max point displacement between kernel and oracle refinements {worst:.2e} m")
-    assert worst <= 2e-4, worst                          # fp32 correspondences vs fp64 kd-tree: sub-0.2 mm agreement
+    assert worst <= 2e-6, worst                          # fp32 correspondences vs fp64 kd-tree (measured <= 6e-8 m)
     assert st[-1, 3] == 0 and np.allclose(T_gpu[-1], np.eye(4))
     # the single-pose drop-in signature
     T1, info1 = icp.icpRefinement(sc["depth"], uvs[0], poses[0], sc["cam_K"], pts, inpaint_depth=False, icp_max_dist=0.01)

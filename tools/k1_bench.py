@@ -36,6 +36,14 @@ if os.environ.get("ZS_CROP", "0") != "0":
         kept.append(c[glue.filterHypoByMask(ob["model_points"], glue.K2meta(sc["cam_K"]), c, mask, th=0.5)])
     P = np.concatenate(kept)[:n_hyp]
     print(f"hypotheses inside box {box} ({box[2]-box[0]} x {box[3]-box[1]} px, {(box[2]-box[0])*(box[3]-box[1])*16/1024:.0f} KB)")
+    if os.environ.get("ZS_CROP_STAGE", "0") != "0":
+        # experiment build (-DZS_CROP_STAGE, run with ZS_LIB=gpurun_ab/libzs_crop.so): stage the centre of the box in
+        # shared memory, at most side x side pixels (104 x 104 x 16 B = 169 KB next to the 36 KB cloud)
+        side = int(os.environ.get("ZS_CROP_SIDE", "104"))
+        w, h = min(side, box[2] - box[0]), min(side, box[3] - box[1])
+        x0, y0 = (box[0] + box[2] - w) // 2, (box[1] + box[3] - h) // 2
+        os.environ["ZS_CROP_RECT"] = f"{x0},{y0},{w},{h}"
+        print(f"crop staged in shared memory: ZS_CROP_RECT={os.environ['ZS_CROP_RECT']} ({w * h * 16 / 1024:.0f} KB)")
 if os.environ.get("ZS_SORT_HYP", "0") == "1":
     # hypotheses ordered by the image tile their translation projects to (what co-resident warps then share in L1)
     K = sc["cam_K"]

@@ -58,17 +58,17 @@ for r in rr[2:]:
     def to_bytes(metric):
         v, u = float(r[idx[metric]].replace(",", "")), units[idx[metric]].lower()
         return int(v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u])
-    key = "zs_pool" if "mlp_tc" in kname else "zs_features" if "features" in kname else kname
+    key = "zs_pool_fp32a" if "mlp_tc3" in kname else "zs_pool" if "mlp_tc" in kname else "zs_features" if "features" in kname else kname
     traffic[key] = {"kernel": kname.replace("void ", "").replace("<unnamed>::", ""),
                     "dram_read_bytes": to_bytes("dram__bytes_read.sum"), "dram_write_bytes": to_bytes("dram__bytes_write.sum")}
 os.makedirs(out_dir, exist_ok=True)
 open(os.path.join(out_dir, f"{tag}_ncu_summary.txt"), "w").write("\n".join(lines) + "\n")
 shutil.copy(launches, os.path.join(out_dir, f"{tag}_launches_c2.csv"))
 tj = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch, from one `ncu --set full --clock-control none` capture of "
-                  f"`{cmd}` (C2, bf16; the captured feature launch = 10,000 hypotheses x 1,000 points of one object, the captured MLP "
-                  f"launch = one 32,768-hypothesis chunk of a scorer's objects).  See {tag}_ncu_summary.txt.  Writes that "
-                  "are still dirty in the 126 MB L2 when the kernel ends are not counted by these counters, hence traffic < "
-                  "algorithmic bytes for the write-heavy feature kernel.",
+                  f"`{cmd}` (C2, bf16).  zs_pool = the first captured launch of the MLP kernel: with the fused kernel all "
+                  "hypotheses of one scorer (110,000 or 100,000 x 1,000 points, no feature rows in HBM: poses in, pooled "
+                  "vectors out, frame and clouds through L2); with --no-fuse one 32,768-hypothesis chunk of bf16 feature rows.  "
+                  f"zs_pool_fp32a = the re-rank's 3-term kernel (88 / 80 hypotheses).  See {tag}_ncu_summary.txt.",
       "workload": "c2", "precision": "bf16"}
 tj.update(traffic)
 json.dump(tj, open(os.path.join(out_dir, f"{tag}_traffic.json"), "w"), indent=2)
