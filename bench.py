@@ -436,6 +436,8 @@ def main():
     roof = {}
     if "pool" in stages:
         st = stages["pool"]
+        if fs._plan.filtered:      # launches are sized by capacity; the MLP runs on the hypotheses that passed the pre-filter
+            st = dict(st, units=scored * n_pts * args.steps)
         flops = 2.0 * MLP_MACS_PER_POINT * st["units"]
         ach = flops / (st["ms"] * 1e-3) / 1e12
         peak = peaks["tensor_sustained"]

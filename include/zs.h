@@ -191,7 +191,8 @@ ZS_API int zs_split_features(zs_ctx* ctx, const float* feat, int n, int n_pts, v
 /* The two halves of zs_score, exposed so that callers can keep the pooled vectors and so that
  * each stage can be timed alone: zs_pool = shared per-point MLP + max over points
  * (pooled_out [dev] float32 [n][1024]; feat_dtype ZS_F32 / ZS_BF16 / ZS_BF16_SPLIT picks the kernel as in zs_score);
- * zs_head = 1024 -> 512 -> 256 -> 1, precision ZS_F32: fp32 on
+ * zs_head = 1024 -> 512 -> 256 -> 1, precision ZS_BF16_SPLIT: fp32-accurate on the tensor cores (3-term tf32 products:
+ * the head of the fp32-accurate path; falls back to the CUDA-core kernels below 1,024 rows), ZS_F32: fp32 on
  * CUDA cores (1e-4 parity path), ZS_BF16: tf32 tensor cores (what zs_score uses after the bf16 MLP). */
 ZS_API int zs_pool(zs_ctx* ctx, int weight_slot, const void* feat, int feat_dtype, int n, int n_pts,
             float* pooled_out, void* stream);

@@ -37,7 +37,7 @@ extern "C" int zs_reserve(zs_ctx* ctx, int max_hypotheses) {
     if (max_hypotheses < 0) return zs_fail(ctx, ZS_ERR_INVALID, "max_hypotheses %d", max_hypotheses);
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t chunk = max_hypotheses < ZS_SCORE_CHUNK ? max_hypotheses : ZS_SCORE_CHUNK;
-    return zs_reserve_ws(ctx, chunk * (1024 + 512 + 256) * sizeof(float));
+    return zs_reserve_ws(ctx, chunk * ZS_HEAD_WS_FLOATS * sizeof(float));
 }
 
 // transforms (n,4,4) float32 or float64, row-major -> poses [n][12] float32 rows of (R | t): the one cast of the
@@ -109,7 +109,7 @@ extern "C" void zs_destroy(zs_ctx* ctx) {
     zs_tc_destroy(ctx);
     cudaFree(ctx->frame.packed);
     for (auto& o : ctx->obj) { cudaFree(o.pA); cudaFree(o.pB); cudaFree(o.pV); }
-    for (auto& w : ctx->w) { cudaFree(w.f32); cudaFree(w.f32t); cudaFree(w.bf16); cudaFree(w.bf16x2); }
+    for (auto& w : ctx->w) { cudaFree(w.f32); cudaFree(w.f32t); cudaFree(w.bf16); cudaFree(w.bf16x2); cudaFree(w.head_lo); }
     cudaFree(ctx->ws);
     cudaFree(ctx->lut255);
     delete ctx;
@@ -286,6 +286,8 @@ extern "C" int zs_set_weights(zs_ctx* ctx, int slot, const float* blob, size_t n
     rc = zs_tc_prepare_weights(ctx, slot, st);
     if (rc) return rc;
     rc = zs_tc3_prepare_weights(ctx, slot, st);
+    if (rc) return rc;
+    rc = zs_head_prepare_weights(ctx, slot, st);
     if (rc) return rc;
     w.set = true;
     return ZS_OK;

@@ -12,6 +12,8 @@
 #include "../../include/zs.h"
 
 #define ZS_SCORE_CHUNK 32768    // hypotheses per scoring chunk (bounds the head's workspace)
+// scratch floats per hypothesis of a chunk: pooled 1024 | g1 512 | g2 256 | lo(pooled) 1024 | lo(g1) 512
+#define ZS_HEAD_WS_FLOATS (1024 + 512 + 256 + 1024 + 512)
 #define ZS_VIOL_MASKED 0x7fffffff   // zs_violations: the hypothesis failed the mask-overlap test (zs_filter never keeps it)
 #define ZS_DEPTH_MARGIN 0.02f   // metres; reference: python/ossid/datasets/ycbv_sift_dataset.py:325
 
@@ -36,6 +38,7 @@ struct zs_weights {
     float* f32t = nullptr;           // transposed ([K][CO]) copies of W1 W2 W3 F1 F2 (zs_score_f32.cu)
     __nv_bfloat16* bf16 = nullptr;   // tensor-core operand images of W1..W3 (see zs_score_tc.cu)
     __nv_bfloat16* bf16x2 = nullptr; // the same as bf16 hi + lo pairs for the fp32-accurate kernel (zs_score_tc3.cu)
+    float* head_lo = nullptr;        // tf32 remainders of F1, F2 for the 3-term tensor-core head (zs_head_tc.cu)
     bool set = false;
 };
 
@@ -75,7 +78,9 @@ int zs_score_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, int n_p
 int zs_tc3_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);  // zs_score_tc3.cu
 int zs_score_tc3(zs_ctx* ctx, int slot, const void* feat_split, int n, int n_pts, float* pooled, float* dbg_h1, float* dbg_h2,
                  cudaStream_t st);
-int zs_head_tc(zs_ctx* ctx, int slot, const float* pooled, int n, float* scores, float* g1, cudaStream_t st);  // zs_head_tc.cu
+int zs_head_tc(zs_ctx* ctx, int slot, const float* pooled, int n, float* scores, float* g1, bool accurate, float* lo_ws,
+               cudaStream_t st);                                             // zs_head_tc.cu
+int zs_head_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);
 int zs_f32_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st);  // zs_score_f32.cu
 
 #define ZS_CUDA(ctx, call)                                                                      \

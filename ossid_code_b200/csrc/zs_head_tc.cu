@@ -84,10 +84,18 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 }
 
 // kFuseOut: instead of storing relu(acc + b), reduce it against `f3` and store one score per row.
-template <bool kFuseOut>
+// n_terms = 3: fp32-accurate GEMM out of tf32 MMAs.  The tensor core reads an fp32 operand as tf32 by ignoring its low 13
+// mantissa bits, i.e. it sees hi(x) = x & 0xffffe000; with lo(x) = x - hi(x) (exact in fp32) the product is accumulated as
+// hi(a).hi(w) + lo(a).hi(w) + hi(a).lo(w): the K loop simply runs three times, over (A, W), (A_lo, W), (A, W_lo).  The
+// dropped lo.lo term and the truncation of lo itself are 2^-20 relative.  out_lo (optional) receives lo(out) so that
+// the next layer needs no extra pass.
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+template <bool kFuseOut, int kTerms>
 __global__ void __launch_bounds__(kThreadsFc, 1)
 zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-           const float* __restrict__ bias, float* __restrict__ out, int n, int K, int CO,
+           const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
+           const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ out_lo, int n, int K, int CO,
            const float* __restrict__ f3, const float* __restrict__ c3) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -98,7 +106,7 @@ zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int co0 = blockIdx.x * kBN, row0 = blockIdx.y * kBM;
-    const int n_kb = K / kBK;
+    const int n_kb1 = K / kBK, n_kb = n_kb1 * kTerms;
 
     if (tid == 0) {
         for (int s = 0; s < kFcStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
@@ -120,8 +128,9 @@ zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 const int s = kb % kFcStages;
                 mbar_wait(empty(s), ((kb / kFcStages) & 1) ^ 1);
                 mbar_expect_tx(full(s), kStageBytes);
-                tma_load_2d(sbase + s * kStageBytes, &map_a, kb * kBK, row0, full(s));
-                tma_load_2d(sbase + s * kStageBytes + kStageA, &map_w, kb * kBK, co0, full(s));
+                const int term = kTerms == 1 ? 0 : kb / n_kb1, kk = kb - term * n_kb1;
+                tma_load_2d(sbase + s * kStageBytes, (kTerms == 3 && term == 1) ? &map_a_lo : &map_a, kk * kBK, row0, full(s));
+                tma_load_2d(sbase + s * kStageBytes + kStageA, (kTerms == 3 && term == 2) ? &map_w_lo : &map_w, kk * kBK, co0, full(s));
             }
         }
     } else if (warp == 1) {
@@ -170,6 +179,9 @@ zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         dot = fmaf(o.z, f.z, dot); dot = fmaf(o.w, f.w, dot);
                     } else if (row < n) {
                         *reinterpret_cast<float4*>(out + (size_t)row * CO + c0 + c) = o;
+                        if (kTerms == 3 && out_lo)
+                            *reinterpret_cast<float4*>(out_lo + (size_t)row * CO + c0 + c) =
+                                make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
                     }
                 }
             }
@@ -214,25 +226,70 @@ int make_map(zs_ctx* ctx, CUtensorMap* map, const float* base, int rows, int K, 
     return ZS_OK;
 }
 
+__global__ void zs_k_tf32_lo(const float4* __restrict__ in, size_t n4, float4* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(in + i);
+        out[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+    }
+}
+
 }  // namespace
 
-// pooled [n][1024] -> scores [n]; g1 [n][512] scratch.  Weights: the fp32 blob of zs_set_weights.
-int zs_head_tc(zs_ctx* ctx, int slot, const float* pooled, int n, float* scores, float* g1, cudaStream_t st) {
+// lo(F1), lo(F2) for the 3-term head, built with the weights
+int zs_head_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st) {
+    zs_weights& w = ctx->w[slot];
+    const size_t n = (size_t)512 * 1024 + (size_t)256 * 512;
+    if (!w.head_lo && cudaMalloc(&w.head_lo, n * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        return zs_fail(ctx, ZS_ERR_NOMEM, "head weight remainders");
+    }
+    zs_k_tf32_lo<<<256, 256, 0, st>>>(reinterpret_cast<const float4*>(w.f32 + ZS_OFF_F1), (size_t)512 * 1024 / 4,
+                                      reinterpret_cast<float4*>(w.head_lo));
+    ZS_LAUNCHED(ctx);
+    zs_k_tf32_lo<<<128, 256, 0, st>>>(reinterpret_cast<const float4*>(w.f32 + ZS_OFF_F2), (size_t)256 * 512 / 4,
+                                      reinterpret_cast<float4*>(w.head_lo + (size_t)512 * 1024));
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
+// pooled [n][1024] -> scores [n]; g1 [n][512] scratch.  accurate: 3-term tf32 products (fp32-level result); then
+// lo_ws [n][1024 + 512] scratch for lo(pooled) and lo(g1).
+int zs_head_tc(zs_ctx* ctx, int slot, const float* pooled, int n, float* scores, float* g1, bool accurate, float* lo_ws,
+               cudaStream_t st) {
     int rc = get_encoder(ctx);
     if (rc) return rc;
     const zs_weights& w = ctx->w[slot];
-    CUtensorMap a1, w1, a2, w2;
+    CUtensorMap a1, w1, a2, w2, a1l, w1l, a2l, w2l;
     if ((rc = make_map(ctx, &a1, pooled, n, 1024, kBM)) || (rc = make_map(ctx, &w1, w.f32 + ZS_OFF_F1, 512, 1024, kBN)) ||
         (rc = make_map(ctx, &a2, g1, n, 512, kBM)) || (rc = make_map(ctx, &w2, w.f32 + ZS_OFF_F2, 256, 512, kBN)))
         return rc;
-    ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_fc_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcSmAlloc));
-    ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_fc_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcSmAlloc));
+    a1l = a1; w1l = w1; a2l = a2; w2l = w2;
+    float* g1_lo = nullptr;
+    if (accurate) {
+        float* p_lo = lo_ws;
+        g1_lo = lo_ws + (size_t)n * 1024;
+        if ((rc = make_map(ctx, &a1l, p_lo, n, 1024, kBM)) || (rc = make_map(ctx, &w1l, w.head_lo, 512, 1024, kBN)) ||
+            (rc = make_map(ctx, &a2l, g1_lo, n, 512, kBM)) ||
+            (rc = make_map(ctx, &w2l, w.head_lo + (size_t)512 * 1024, 256, 512, kBN)))
+            return rc;
+        const size_t n4 = (size_t)n * 1024 / 4;
+        zs_k_tf32_lo<<<(unsigned)((n4 + 255) / 256 < 4096 ? (n4 + 255) / 256 : 4096), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(pooled), n4, reinterpret_cast<float4*>(p_lo));
+        ZS_LAUNCHED(ctx);
+    }
     const int row_tiles = (n + kBM - 1) / kBM;
-    zs_k_fc_tc<false><<<dim3(512 / kBN, row_tiles), kThreadsFc, kFcSmAlloc, st>>>(a1, w1, w.f32 + ZS_OFF_C1, g1, n, 1024, 512,
-                                                                               nullptr, nullptr);
-    ZS_LAUNCHED(ctx);
-    zs_k_fc_tc<true><<<dim3(256 / kBN, row_tiles), kThreadsFc, kFcSmAlloc, st>>>(a2, w2, w.f32 + ZS_OFF_C2, scores, n, 512, 256,
-                                                                              w.f32 + ZS_OFF_F3, w.f32 + ZS_OFF_C3);
-    ZS_LAUNCHED(ctx);
+#define ZS_LAUNCH_HEAD(TERMS)                                                                                                  \
+    do {                                                                                                                       \
+        ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_fc_tc<false, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcSmAlloc)); \
+        ZS_CUDA(ctx, cudaFuncSetAttribute(zs_k_fc_tc<true, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcSmAlloc));  \
+        zs_k_fc_tc<false, TERMS><<<dim3(512 / kBN, row_tiles), kThreadsFc, kFcSmAlloc, st>>>(                                   \
+            a1, w1, a1l, w1l, w.f32 + ZS_OFF_C1, g1, g1_lo, n, 1024, 512, nullptr, nullptr);                                    \
+        ZS_LAUNCHED(ctx);                                                                                                      \
+        zs_k_fc_tc<true, TERMS><<<dim3(256 / kBN, row_tiles), kThreadsFc, kFcSmAlloc, st>>>(                                    \
+            a2, w2, a2l, w2l, w.f32 + ZS_OFF_C2, scores, nullptr, n, 512, 256, w.f32 + ZS_OFF_F3, w.f32 + ZS_OFF_C3);           \
+        ZS_LAUNCHED(ctx);                                                                                                      \
+    } while (0)
+    if (accurate) ZS_LAUNCH_HEAD(3); else ZS_LAUNCH_HEAD(1);
+#undef ZS_LAUNCH_HEAD
     return ZS_OK;
 }

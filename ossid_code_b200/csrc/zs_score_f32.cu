@@ -185,13 +185,19 @@ zs_k_fc_small(const float* __restrict__ in, const float* __restrict__ Wt, const 
 #pragma unroll
     for (int r = 0; r < kSmallRows; ++r) acc[r] = 0.f;
     const int kq = K / 4;
-#pragma unroll 4
-    for (int k = ks * kq; k < (ks + 1) * kq; ++k) {
-        const float w = __ldg(Wt + (size_t)k * CO + co);
-        const float4 a0 = *reinterpret_cast<const float4*>(in_t + k * kSmallRows);
-        const float4 a1 = *reinterpret_cast<const float4*>(in_t + k * kSmallRows + 4);
-        acc[0] = fmaf(w, a0.x, acc[0]); acc[1] = fmaf(w, a0.y, acc[1]); acc[2] = fmaf(w, a0.z, acc[2]); acc[3] = fmaf(w, a0.w, acc[3]);
-        acc[4] = fmaf(w, a1.x, acc[4]); acc[5] = fmaf(w, a1.y, acc[5]); acc[6] = fmaf(w, a1.z, acc[6]); acc[7] = fmaf(w, a1.w, acc[7]);
+    // the weight column is the only global read of the loop: keep eight loads in flight (the loop is bound by their L2
+    // latency, not by the 8 FMAs per weight)
+    for (int k0 = ks * kq; k0 < (ks + 1) * kq; k0 += 8) {
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(Wt + (size_t)(k0 + u) * CO + co);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 a0 = *reinterpret_cast<const float4*>(in_t + (k0 + u) * kSmallRows);
+            const float4 a1 = *reinterpret_cast<const float4*>(in_t + (k0 + u) * kSmallRows + 4);
+            acc[0] = fmaf(w[u], a0.x, acc[0]); acc[1] = fmaf(w[u], a0.y, acc[1]); acc[2] = fmaf(w[u], a0.z, acc[2]); acc[3] = fmaf(w[u], a0.w, acc[3]);
+            acc[4] = fmaf(w[u], a1.x, acc[4]); acc[5] = fmaf(w[u], a1.y, acc[5]); acc[6] = fmaf(w[u], a1.z, acc[6]); acc[7] = fmaf(w[u], a1.w, acc[7]);
+        }
     }
 #pragma unroll
     for (int r = 0; r < kSmallRows; ++r) part[(ks * kSmallRows + r) * kSmallCo + c] = acc[r];
@@ -256,7 +262,9 @@ int zs_f32_prepare_weights(zs_ctx* ctx, int slot, cudaStream_t st) {
 // pooled [m][1024] -> scores [m]; g1 [m][512], g2 [m][256] scratch.
 static int head_impl(zs_ctx* ctx, int slot, const float* pooled, int n, float* scores, float* g1, float* g2,
                      int precision, cudaStream_t st) {
-    if (precision == ZS_BF16) return zs_head_tc(ctx, slot, pooled, n, scores, g1, st);   // tensor cores (tf32)
+    if (precision == ZS_BF16) return zs_head_tc(ctx, slot, pooled, n, scores, g1, false, nullptr, st);   // tensor cores (tf32)
+    if (precision == ZS_BF16_SPLIT && n > 1024)                      // fp32-accurate on the tensor cores (3-term tf32)
+        return zs_head_tc(ctx, slot, pooled, n, scores, g1, true, g2 + (size_t)n * 256, st);
     const zs_weights& w = ctx->w[slot];
     if (n <= 1024) {         // a handful of rows (the re-rank): small tiles so that the whole GPU takes part
         const int tiles = (n + kSmallRows - 1) / kSmallRows;
@@ -323,15 +331,16 @@ extern "C" int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n,
     if (!ctx) return ZS_ERR_INVALID;
     if (weight_slot < 0 || weight_slot >= ZS_MAX_WEIGHT_SLOTS || !ctx->w[weight_slot].set)
         return zs_fail(ctx, ZS_ERR_STATE, "weight slot %d not set", weight_slot);
-    if (n < 0 || (precision != ZS_F32 && precision != ZS_BF16) || (n > 0 && (!pooled || !scores_out || ((uintptr_t)pooled & 15))))
+    if (n < 0 || (precision != ZS_F32 && precision != ZS_BF16 && precision != ZS_BF16_SPLIT) ||
+        (n > 0 && (!pooled || !scores_out || ((uintptr_t)pooled & 15))))
         return zs_fail(ctx, ZS_ERR_INVALID, "zs_head arguments");
     if (n == 0) return ZS_OK;
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     const int chunk = n < kScoreChunk ? n : kScoreChunk;
-    int rc = zs_reserve_ws(ctx, (size_t)chunk * (1024 + 512 + 256) * sizeof(float));
+    int rc = zs_reserve_ws(ctx, (size_t)chunk * ZS_HEAD_WS_FLOATS * sizeof(float));
     if (rc) return rc;
     float* g1 = (float*)ctx->ws + (size_t)chunk * 1024;
-    float* g2 = g1 + (size_t)chunk * 512;
+    float* g2 = g1 + (size_t)chunk * 512;      // followed by the lo(pooled) | lo(g1) scratch of the 3-term head
     for (int s = 0; s < n; s += chunk) {
         const int m = (n - s) < chunk ? (n - s) : chunk;
         rc = head_impl(ctx, weight_slot, pooled + (size_t)s * 1024, m, scores_out + s, g1, g2, precision, (cudaStream_t)stream);
@@ -352,7 +361,7 @@ extern "C" int zs_score(zs_ctx* ctx, int weight_slot, const void* feat, int feat
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int chunk = n < kScoreChunk ? n : kScoreChunk;
-    rc = zs_reserve_ws(ctx, (size_t)chunk * (1024 + 512 + 256) * sizeof(float));
+    rc = zs_reserve_ws(ctx, (size_t)chunk * ZS_HEAD_WS_FLOATS * sizeof(float));
     if (rc) return rc;
     float* pooled = (float*)ctx->ws;
     float* g1 = pooled + (size_t)chunk * 1024;
@@ -362,7 +371,8 @@ extern "C" int zs_score(zs_ctx* ctx, int weight_slot, const void* feat, int feat
         const int m = (n - s) < chunk ? (n - s) : chunk;
         rc = pool_impl(ctx, weight_slot, (const char*)feat + (size_t)s * n_pts * 8 * esz, feat_dtype, m, n_pts, pooled, st);
         if (rc) return rc;
-        rc = head_impl(ctx, weight_slot, pooled, m, scores_out + s, g1, g2, precision, st);
+        rc = head_impl(ctx, weight_slot, pooled, m, scores_out + s, g1, g2,
+                       feat_dtype == ZS_BF16_SPLIT ? ZS_BF16_SPLIT : precision, st);   // split path: tensor-core head as well
         if (rc) return rc;
     }
     return ZS_OK;

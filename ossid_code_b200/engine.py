@@ -345,12 +345,13 @@ class ZsContext:
         self._ck(self.lib.zs_pool_fused(self.h, wslot, n, slots, poses, counts, out.data_ptr(), self._stream()), "zs_pool_fused")
         return out
 
-    def head(self, wslot: int, pooled: torch.Tensor, tensor_cores: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """(n,1024) pooled -> (n,) scores; tensor_cores=True: tf32 tcgen05 GEMMs, False: fp32 CUDA cores."""
+    def head(self, wslot: int, pooled: torch.Tensor, tensor_cores, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(n,1024) pooled -> (n,) scores; tensor_cores=True / "tf32": tf32 tcgen05 GEMMs (the bf16 path's head);
+        "fp32_tc": fp32-accurate 3-term tf32 tcgen05 GEMMs; False / "fp32": fp32 CUDA cores."""
         n = pooled.shape[0]
         scores = out if out is not None else torch.empty((n,), dtype=torch.float32, device=self.device)
-        self._ck(self.lib.zs_head(self.h, wslot, pooled.data_ptr(), n, ZS_BF16 if tensor_cores else ZS_F32,
-                                  scores.data_ptr(), self._stream()), "zs_head")
+        code = {True: ZS_BF16, "tf32": ZS_BF16, "fp32_tc": ZS_BF16_SPLIT, False: ZS_F32, "fp32": ZS_F32}[tensor_cores]
+        self._ck(self.lib.zs_head(self.h, wslot, pooled.data_ptr(), n, code, scores.data_ptr(), self._stream()), "zs_head")
         return scores
 
     def pool_debug(self, wslot: int, feat: torch.Tensor):

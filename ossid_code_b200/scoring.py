@@ -426,7 +426,7 @@ class FrameScorer:
         ctx, k = self.ctx, self.k
         res, plan = self._resident, self._plan
         n_obj, nk = plan.n_obj, plan.n_obj * k
-        head_tc = not self.split              # tf32 tensor-core head on the bf16 path, fp32 CUDA-core head on the 1e-4 path
+        head_tc = "fp32_tc" if self.split else "tf32"   # tf32 head on the bf16 path, 3-term tf32 (fp32-accurate) on the 1e-4 path
         self._sync_weights()
         rec = plan.rec
         S_loc, I_loc = rec[:nk].view(torch.float32).view(n_obj, k), rec[nk:2 * nk].view(n_obj, k)

@@ -22,7 +22,7 @@ def _head_ref(pooled, w, tf32):
     return (g @ w["F3"].T + w["c3"])[:, 0]
 
 
-@pytest.mark.parametrize("n", [1, 127, 128, 129, 1000, 33000])
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 1000, 1025, 2000, 33000])
 def test_head_tensor_core_matches_oracle(ctx, n):
     g = torch.Generator().manual_seed(n)
     pooled = torch.relu(torch.randn(n, 1024, generator=g)) * 2.0          # pooled vectors are post-ReLU
@@ -34,6 +34,9 @@ def test_head_tensor_core_matches_oracle(ctx, n):
     ref32, reftf = _head_ref(pooled, w, False), _head_ref(pooled, w, True)
     scale = float(ref32.abs().max())
     assert float((f32 - ref32).abs().max()) <= 1e-4 * scale + 1e-6, "fp32 CUDA-core head"
+    acc = ctx.head(2, dev, tensor_cores="fp32_tc").cpu()          # 3-term tf32 on the tensor cores (CUDA cores below 1,025 rows)
+    e_acc = float((acc - ref32).abs().max())
+    assert e_acc <= 2e-5 * scale + 1e-6, f"fp32-accurate tensor-core head: {e_acc:.3e} (scale {scale:.2f})"
     e_tf, e_32 = float((tc - reftf).abs().max()), float((tc - ref32).abs().max())
     print(f"n={n}: tf32 head vs tf32 oracle {e_tf:.3e}, vs fp32 oracle {e_32:.3e}, scale {scale:.2f}")
     assert e_tf <= 1e-3 * scale + 1e-6, "tf32 tensor-core head vs tf32-emulating oracle"
