@@ -85,8 +85,9 @@ class ScoreDataset:
     """``ScoreDataset(datapoints, dataset_root, dataset_name, args, mode='test')`` -- featuriser only.
 
     Honoured ``args`` fields: ``inconst_ratio_th`` (online_learning.py:195), plus two of this
-    build: ``zs_precision`` ("fp32" -> float32 features, scored to 1e-4 by the 3-term bf16-split tcgen05 scorer;
-    "bf16" (default) -> bfloat16 features + bf16 tcgen05 scorer, 1e-2) and ``zs_device``.
+    build: ``zs_precision`` ("fp32" (default) -> float32 features, scored to 1e-4 by the 3-term bf16-split tcgen05
+    scorer, so that ``scores.argmax()`` (online_learning.py:466-467) is the fp32 argmax; "bf16" -> bfloat16 features +
+    bf16 tcgen05 scorer, 1e-2, three times the throughput) and ``zs_device``.
     """
 
     dim_point = W.DIM_POINT
@@ -96,7 +97,7 @@ class ScoreDataset:
         self.args, self.mode, self.dataset_name = args, mode, dataset_name
         th = getattr(args, "inconst_ratio_th", None)
         self.inconst_ratio_th = 100.0 if th is None else float(th)
-        prec = getattr(args, "zs_precision", "bf16")
+        prec = getattr(args, "zs_precision", "fp32")
         if prec not in ("fp32", "bf16"):
             raise ValueError(f"zs_precision must be 'fp32' or 'bf16', got {prec!r}")
         self.feature_dtype = torch.float32 if prec == "fp32" else torch.bfloat16
