@@ -221,8 +221,8 @@ def config_for(args, world, scaling):
     return {"workload": f"{args.workload}: {desc}", "hypotheses_per_step": n_obj * per_gpu * mult * n_frames,
             "frames_per_step": n_frames, "objects": n_obj, "points_per_object": n_pts, "topk": args.k,
             "inconst_ratio_th": args.inconst_th,
-            "kernels": ("fused projection+gather+features+MLP+max-pool kernel" if (args.precision == "bf16" and not args.no_fuse
-                        and args.inconst_th >= 100 and args.workload != "c3f") else "zs_features -> zs_pool (features through HBM)"),
+            "kernels": ("fused projection+gather+features+MLP+max-pool kernel" if (args.precision == "bf16" and not args.no_fuse)
+                        else "zs_features -> zs_pool (features through HBM)"),
             "parallelism": (f"hypothesis-sharded x{world}, one all-gather of top-k records" if world > 1 else "single GPU"),
             "l2": "feature chunks of 32768 hypotheses x 1000 pts (>= 0.5 GB) exceed the 126 MB L2; no flush needed",
             "weights": "seeded random (no checkpoint is published)"}
@@ -470,7 +470,7 @@ def main():
                                      "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
                                      "traffic": None, "peak_source": peaks["source"], "launch_groups": st["calls"],
                                      "ms_in_timed_region": st["ms"], "share_of_step": st["ms"] / timed_ms}
-    for key in ("head", "topk", "rerank", "allgather+merge"):
+    for key in ("prefilter", "head", "topk", "rerank", "allgather+merge"):
         if key in stages:
             roof[f"{key}_share_of_step"] = stages[key]["ms"] / timed_ms
             roof[f"{key}_ms_per_step"] = stages[key]["ms"] / args.steps

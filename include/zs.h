@@ -149,6 +149,16 @@ ZS_API int zs_boxes_to_mask(zs_ctx* ctx, const double* boxes, const double* scor
 ZS_API int zs_filter(zs_ctx* ctx, const int32_t* viol, int n, int n_pts, float inconst_ratio_th,
               int32_t* keep_idx_out, int32_t* n_keep_out, int32_t* info_out, void* stream);
 
+/* zs_violations + zs_filter for ALL objects of a frame in two launches (one projection / depth-gather pass over every
+ * segment, then one CTA per object for the compaction): segment i = n_hyp[i] hypotheses poses[i] of the cloud in
+ * obj_slots[i], optional masks[i] (nullable array / entries) tested with mask_th as in zs_violations, kept by
+ * inconst_ratio_th as in zs_filter.  viol_out[i] [dev] int32 [n_hyp[i]], keep_idx_out[i] [dev] int32 [n_hyp[i]],
+ * n_keep_out[i] [dev] int32[1], info_out[i] [dev] int32[2] (nullable).  All array arguments are [host] arrays of n_seg
+ * (<= ZS_MAX_OBJECTS) entries. */
+ZS_API int zs_prefilter(zs_ctx* ctx, int n_seg, const int32_t* obj_slots, const float* const* poses, const int32_t* n_hyp,
+                 const uint8_t* const* masks, double mask_th, float inconst_ratio_th, int32_t* const* viol_out,
+                 int32_t* const* keep_idx_out, int32_t* const* n_keep_out, int32_t* const* info_out, void* stream);
+
 /* Device-side hypothesis count for the calls that follow (no host read-back of zs_filter's count, so a filtered frame
  * stays asynchronous): while n_dev [dev] int32[1] is set, zs_features (n_keep) and zs_pool with bf16 features (n)
  * treat their count argument as a CAPACITY and process entries [n_offset, n_offset + capacity) of a list that has
@@ -202,11 +212,16 @@ ZS_API int zs_head(zs_ctx* ctx, int weight_slot, const float* pooled, int n, int
 /* zs_features + zs_pool (bf16 tensor-core path) in ONE kernel: the producer warps of the MLP kernel project, gather and
  * featurise each 128-point tile themselves and hand it to the tensor cores through shared memory, so the feature rows
  * never travel through HBM.  The hypothesis list is the concatenation of n_seg segments: segment i = n_hyp[i]
- * hypotheses of the cloud in obj_slots[i] with poses[i] [dev] float32 [n_hyp[i]][12] (obj_slots / poses / n_hyp are
- * [host] arrays); all clouds of a call have the same number of points (>= 128).  pooled_out [dev] float32
- * [sum n_hyp][1024], bit-identical to zs_features(ZS_BF16) followed by zs_pool. */
+ * hypotheses of the cloud in obj_slots[i]; hypothesis j of the segment is pose keep_idx[i][j] of poses[i] [dev] float32
+ * [..][12] (keep_idx NULL or keep_idx[i] NULL: pose j).  n_dev (nullable, entries nullable): [dev] int32[1] per segment,
+ * the device-side count of zs_filter; then n_hyp[i] is the segment's CAPACITY and min(n_hyp[i], *n_dev[i]) hypotheses
+ * are scored.  obj_slots / poses / keep_idx / n_hyp / n_dev are [host] arrays of n_seg entries.  All clouds of a call
+ * have the same number of points (>= 128).  pooled_out [dev] float32 [sum n_hyp][1024]: segment i's rows start at
+ * sum(n_hyp[0..i)) (rows beyond a device-side count are left untouched); bit-identical to zs_features(ZS_BF16)
+ * followed by zs_pool. */
 ZS_API int zs_pool_fused(zs_ctx* ctx, int weight_slot, int n_seg, const int32_t* obj_slots, const float* const* poses,
-                  const int32_t* n_hyp, float* pooled_out, void* stream);
+                  const int32_t* const* keep_idx, const int32_t* n_hyp, const int32_t* const* n_dev,
+                  float* pooled_out, void* stream);
 
 /* Diagnostic twin of zs_pool for ZS_BF16 / ZS_BF16_SPLIT features: additionally dumps the activations of layers 1
  * and 2 as the next layer reads them (h1_out [dev] float32 [n*n_pts][64], h2_out [dev] float32 [n*n_pts][128];

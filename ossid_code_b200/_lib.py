@@ -30,6 +30,7 @@ SIGNATURES = {
     "zs_mask_count": (_i, [_p, _p, _i, _p, _i, _f, _f, _f, _f, _p, _i, _i, _p, _p]),
     "zs_violations": (_i, [_p, _i, _p, _i, _p, C.c_double, _p, _p]),
     "zs_boxes_to_mask": (_i, [_p, _p, _p, _i, C.c_double, _p, _p]),
+    "zs_prefilter": (_i, [_p, _i, _p, _p, _p, _p, C.c_double, _f, _p, _p, _p, _p, _p]),
     "zs_filter": (_i, [_p, _p, _i, _i, _f, _p, _p, _p, _p]),
     "zs_reserve": (_i, [_p, _i]),
     "zs_pack_poses": (_i, [_p, _p, _i, _i, _p, _p]),
@@ -41,7 +42,7 @@ SIGNATURES = {
     "zs_split_features": (_i, [_p, _p, _i, _i, _p, _p]),
     "zs_pool": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "zs_head": (_i, [_p, _i, _p, _i, _i, _p, _p]),
-    "zs_pool_fused": (_i, [_p, _i, _i, _p, _p, _p, _p, _p]),
+    "zs_pool_fused": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "zs_pool_debug": (_i, [_p, _i, _p, _i, _i, _i, _p, _p, _p, _p]),
     "zs_pose_errors": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _p]),
     "zs_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),

@@ -395,6 +395,48 @@ zs_k_features_multi(const __grid_constant__ feat_segs segs, int n_seg, zs_cam ca
 // hypothesis as soon as the points still to come cannot lift it over that bar (early-out: a hypothesis far from the
 // detector's box is dropped after about half of its projections and without the rest of its depth gathers) and
 // reports ZS_VIOL_MASKED instead of a count.
+// One hypothesis, one warp: lanes stride over the model points, two points per lane per iteration (two gathers in flight).
+template <bool kSmem, bool kMask>
+__device__ __forceinline__ int viol_hypothesis(int N, const zs_cam& cam, const float* __restrict__ frame_d, const zs_pose& T,
+                                               const float4* sA, const uint8_t* __restrict__ mask, int mask_min, int lane) {
+    const float fW = (float)cam.W, fH = (float)cam.H;
+    int viol = 0, in_mask = 0;
+    for (int p0 = 0; p0 < N; p0 += 64) {
+        float z[2], d[2];
+        bool need_d[2], im[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int p = p0 + j * 32 + lane;
+            need_d[j] = im[j] = false;
+            z[j] = d[j] = 0.f;
+            if (p < N) {
+                const float4 a = kSmem ? sA[p] : __ldg(sA + p);
+                float x, y, ur, vr;
+                zs_transform(T, a.x, a.y, a.z, x, y, z[j]);
+                zs_project(cam, x, y, z[j], ur, vr);
+                const bool in_frame = (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
+                const size_t pix = in_frame ? (size_t)(int)vr * cam.W + (int)ur : 0;
+                if (kMask && in_frame) im[j] = __ldg(mask + pix) != 0;                 // no z test: zephyr_utils.py:58-66
+                need_d[j] = in_frame && (z[j] > 0.f) && (z[j] <= kFltMax);
+                if (need_d[j]) d[j] = __ldg(frame_d + 4 * pix);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const bool fs = need_d[j] && (d[j] > 0.f) && (d[j] <= kFltMax) && (xsub(d[j], z[j]) > ZS_DEPTH_MARGIN);
+            viol += __popc(__ballot_sync(0xffffffffu, fs));
+            if (kMask) in_mask += __popc(__ballot_sync(0xffffffffu, im[j]));
+        }
+        if (kMask && in_mask + max(N - (p0 + 64), 0) < mask_min) return ZS_VIOL_MASKED;   // warp-uniform early-out
+    }
+    return viol;
+}
+
+// kMask: the hypothesis must also project at least `mask_min` of its points onto non-zero pixels of `mask`
+// (filterHypoByMask, python/ossid/utils/zephyr_utils.py:49-71; bounds predicate :61-62).  The warp stops working on a
+// hypothesis as soon as the points still to come cannot lift it over that bar (early-out: a hypothesis far from the
+// detector's box is dropped after about half of its projections and without the rest of its depth gathers) and
+// reports ZS_VIOL_MASKED instead of a count.
 template <bool kSmem, bool kMask>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 zs_k_violations(obj_view o, zs_cam cam, const float4* __restrict__ frame, const float* __restrict__ poses,
@@ -407,35 +449,47 @@ zs_k_violations(obj_view o, zs_cam cam, const float4* __restrict__ frame, const 
     const int warps_per_cta = blockDim.x >> 5;
     const int warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * warps_per_cta;
-    const int N = o.n_pts;
-    const float fW = (float)cam.W, fH = (float)cam.H;
-    const float* frame_d = reinterpret_cast<const float*>(frame);
     for (int h = warp; h < n; h += n_warps) {
-        const zs_pose T = zs_load_pose(poses, h);
-        int viol = 0, in_mask = 0;
-        bool rejected = false;
-        for (int p0 = 0; p0 < N; p0 += 32) {
-            const int p = p0 + lane;
-            bool fs = false, im = false;
-            if (p < N) {
-                const float4 a = kSmem ? sA[p] : __ldg(sA + p);
-                float x, y, z, ur, vr;
-                zs_transform(T, a.x, a.y, a.z, x, y, z);
-                zs_project(cam, x, y, z, ur, vr);
-                const bool in_frame = (ur >= 0.f) && (ur < fW) && (vr >= 0.f) && (vr < fH);
-                if (kMask && in_frame) im = __ldg(mask + (size_t)(int)vr * cam.W + (int)ur) != 0;   // no z test: zephyr_utils.py:58-66
-                if (in_frame && (z > 0.f) && (z <= kFltMax)) {
-                    const float d = __ldg(frame_d + 4 * ((size_t)(int)vr * cam.W + (int)ur));
-                    fs = (d > 0.f) && (d <= kFltMax) && (xsub(d, z) > ZS_DEPTH_MARGIN);
-                }
-            }
-            viol += __popc(__ballot_sync(0xffffffffu, fs));
-            if (kMask) {
-                in_mask += __popc(__ballot_sync(0xffffffffu, im));
-                if (in_mask + max(N - (p0 + 32), 0) < mask_min) { rejected = true; break; }           // warp-uniform
-            }
+        const int v = viol_hypothesis<kSmem, kMask>(o.n_pts, cam, reinterpret_cast<const float*>(frame), zs_load_pose(poses, h),
+                                                    sA, mask, mask_min, lane);
+        if (lane == 0) viol_out[h] = v;
+    }
+}
+
+// The pre-filter pass of a whole frame in one launch: segment i = (cloud, poses, count[, mask]) -> viol_out[i].
+struct viol_seg {
+    obj_view o;
+    const float* poses;
+    const uint8_t* mask;
+    int32_t* viol_out;
+    int n, mask_min;
+};
+struct viol_segs { viol_seg s[kMaxSegsPerLaunch]; };
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+zs_k_violations_multi(const __grid_constant__ viol_segs segs, int n_seg, zs_cam cam, const float4* __restrict__ frame) {
+    extern __shared__ __align__(16) char smem[];
+    const int lane = threadIdx.x & 31;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int n_warps = gridDim.x * warps_per_cta;
+    const int stride_ctas = max(1, (int)gridDim.x / n_seg);
+    for (int sgi = 0; sgi < n_seg; ++sgi) {
+        const viol_seg& sg = segs.s[sgi];
+        const int cta_first = (int)(((long long)blockIdx.x + gridDim.x - (long long)(sgi * stride_ctas) % gridDim.x) % gridDim.x);
+        if (cta_first * warps_per_cta >= sg.n) continue;                          // CTA-uniform
+        float4 *sA, *sB;
+        float* sV;
+        __syncthreads();                                                           // previous segment's cloud no longer in use
+        stage_cloud<kSmem>(sg.o, sA, sB, sV, smem);
+        for (int h = cta_first * warps_per_cta + (threadIdx.x >> 5); h < sg.n; h += n_warps) {
+            const zs_pose T = zs_load_pose(sg.poses, h);
+            const int v = sg.mask ? viol_hypothesis<kSmem, true>(sg.o.n_pts, cam, reinterpret_cast<const float*>(frame), T, sA,
+                                                                 sg.mask, sg.mask_min, lane)
+                                  : viol_hypothesis<kSmem, false>(sg.o.n_pts, cam, reinterpret_cast<const float*>(frame), T, sA,
+                                                                  nullptr, 0, lane);
+            if (lane == 0) sg.viol_out[h] = v;
         }
-        if (lane == 0) viol_out[h] = rejected ? ZS_VIOL_MASKED : viol;
     }
 }
 
@@ -487,9 +541,29 @@ zs_k_project(const float* __restrict__ poses, int n, const float* __restrict__ p
 // ---------------------------------------------------------------------------------------
 // Hypothesis pre-filter: stable compaction of {h : viol[h]*100/n_pts < th}; single CTA.
 // ---------------------------------------------------------------------------------------
+struct filt_seg { const int32_t* viol; int32_t* keep_idx; int32_t* n_keep_out; int32_t* info_out; int n; float n_pts_f; };
+struct filt_segs { filt_seg s[ZS_MAX_OBJECTS]; };
+
+__device__ __forceinline__ void filter_body(const int32_t* __restrict__ viol, int n, float n_pts_f, float th,
+                                            int32_t* __restrict__ keep_idx, int32_t* __restrict__ n_keep_out,
+                                            int32_t* __restrict__ info_out);
+
 __global__ void __launch_bounds__(1024)
 zs_k_filter(const int32_t* __restrict__ viol, int n, float n_pts_f, float th, int32_t* __restrict__ keep_idx,
             int32_t* __restrict__ n_keep_out, int32_t* __restrict__ info_out) {
+    filter_body(viol, n, n_pts_f, th, keep_idx, n_keep_out, info_out);
+}
+
+// one CTA per object of the frame
+__global__ void __launch_bounds__(1024)
+zs_k_filter_multi(const __grid_constant__ filt_segs segs, float th) {
+    const filt_seg& g = segs.s[blockIdx.x];
+    filter_body(g.viol, g.n, g.n_pts_f, th, g.keep_idx, g.n_keep_out, g.info_out);
+}
+
+__device__ __forceinline__ void filter_body(const int32_t* __restrict__ viol, int n, float n_pts_f, float th,
+                                            int32_t* __restrict__ keep_idx, int32_t* __restrict__ n_keep_out,
+                                            int32_t* __restrict__ info_out) {
     __shared__ int s_warp[32];
     __shared__ int s_total;
     __shared__ unsigned long long s_min;
@@ -714,6 +788,14 @@ extern "C" int zs_features_multi(zs_ctx* ctx, int n_seg, const int32_t* obj_slot
     return ZS_OK;
 }
 
+static int mask_min_count(double mask_th, int n_pts) {
+    // smallest in-mask count c that the reference keeps: c / N > th in float64 (zephyr_utils.py:68-70)
+    int c = (int)floor(mask_th * (double)n_pts) - 1;
+    if (c < 0) c = 0;
+    while (c <= n_pts && !((double)c / (double)n_pts > mask_th)) ++c;
+    return c;
+}
+
 extern "C" int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int n, const uint8_t* mask, double mask_th,
                              int32_t* viol_out, void* stream) {
     obj_view o;
@@ -723,13 +805,7 @@ extern "C" int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int 
     if (rc) return rc;
     if (n < 0 || !viol_out) return zs_fail(ctx, ZS_ERR_INVALID, "n %d", n);
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
-    // smallest in-mask count c that the reference keeps: c / N > th in float64 (zephyr_utils.py:68-70)
-    int mask_min = 0;
-    if (mask) {
-        mask_min = (int)floor((double)mask_th * (double)o.n_pts) - 1;
-        if (mask_min < 0) mask_min = 0;
-        while (mask_min <= o.n_pts && !((double)mask_min / (double)o.n_pts > (double)mask_th)) ++mask_min;
-    }
+    const int mask_min = mask ? mask_min_count(mask_th, o.n_pts) : 0;
     const bool in_smem = cloud_smem(o.n_pts) <= kCloudSmemMax;
     const cta_shape cs = shape_for(in_smem ? cloud_smem(o.n_pts) : 0, 0);
     const int grid = grid_for(ctx, n, cs.ctas_per_sm, cs.threads / 32);
@@ -743,6 +819,62 @@ extern "C" int zs_violations(zs_ctx* ctx, int obj_slot, const float* poses, int 
     if (in_smem) { if (mask) ZS_LAUNCH_VIOL(true, true); else ZS_LAUNCH_VIOL(true, false); }
     else         { if (mask) ZS_LAUNCH_VIOL(false, true); else ZS_LAUNCH_VIOL(false, false); }
 #undef ZS_LAUNCH_VIOL
+    ZS_LAUNCHED(ctx);
+    return ZS_OK;
+}
+
+extern "C" int zs_prefilter(zs_ctx* ctx, int n_seg, const int32_t* obj_slots, const float* const* poses, const int32_t* n_hyp,
+                            const uint8_t* const* masks, double mask_th, float inconst_ratio_th, int32_t* const* viol_out,
+                            int32_t* const* keep_idx_out, int32_t* const* n_keep_out, int32_t* const* info_out, void* stream) {
+    if (!ctx) return ZS_ERR_INVALID;
+    if (n_seg == 0) return ZS_OK;
+    if (n_seg < 0 || n_seg > ZS_MAX_OBJECTS || !obj_slots || !poses || !n_hyp || !viol_out || !keep_idx_out || !n_keep_out)
+        return zs_fail(ctx, ZS_ERR_INVALID, "zs_prefilter arguments (%d segments, at most %d)", n_seg, ZS_MAX_OBJECTS);
+    ZS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    filt_segs fsegs;
+    zs_cam cam;
+    for (int s0 = 0; s0 < n_seg; s0 += kMaxSegsPerLaunch) {
+        viol_segs vs;
+        int m = 0, max_pts = 0;
+        long long units = 0;
+        for (int i = s0; i < n_seg && i < s0 + kMaxSegsPerLaunch; ++i) {
+            if (n_hyp[i] < 0 || !n_keep_out[i] || (n_hyp[i] > 0 && (!viol_out[i] || !keep_idx_out[i])))
+                return zs_fail(ctx, ZS_ERR_INVALID, "segment %d: n_hyp %d / null output", i, n_hyp[i]);
+            if (n_hyp[i] == 0) continue;
+            obj_view o;
+            int rc = check_obj(ctx, obj_slots[i], poses[i], o, cam);
+            if (rc) return rc;
+            viol_seg& g = vs.s[m++];
+            g.o = o;
+            g.poses = poses[i];
+            g.mask = masks ? masks[i] : nullptr;
+            g.viol_out = viol_out[i];
+            g.n = n_hyp[i];
+            g.mask_min = g.mask ? mask_min_count(mask_th, o.n_pts) : 0;
+            max_pts = o.n_pts > max_pts ? o.n_pts : max_pts;
+            units += n_hyp[i];
+        }
+        if (m == 0) continue;
+        const bool in_smem = cloud_smem(max_pts) <= kCloudSmemMax;
+        const cta_shape cs = shape_for(in_smem ? cloud_smem(max_pts) : 0, 0);
+        int grid = grid_for(ctx, units, cs.ctas_per_sm, cs.threads / 32);
+        if (grid < m) grid = m < ctx->sm_count ? m : ctx->sm_count;
+        if (in_smem) {
+            int rc = opt_in_smem(ctx, zs_k_violations_multi<true>, cs.smem);
+            if (rc) return rc;
+            zs_k_violations_multi<true><<<grid, cs.threads, cs.smem, st>>>(vs, m, cam, ctx->frame.packed);
+        } else {
+            zs_k_violations_multi<false><<<grid, cs.threads, 0, st>>>(vs, m, cam, ctx->frame.packed);
+        }
+        ZS_LAUNCHED(ctx);
+    }
+    for (int i = 0; i < n_seg; ++i) {
+        const int npts = (obj_slots[i] >= 0 && obj_slots[i] < ZS_MAX_OBJECTS) ? ctx->obj[obj_slots[i]].n_pts : 0;
+        fsegs.s[i] = filt_seg{viol_out[i], keep_idx_out[i], n_keep_out[i], info_out ? info_out[i] : nullptr, n_hyp[i],
+                              (float)(npts > 0 ? npts : 1)};
+    }
+    zs_k_filter_multi<<<n_seg, 1024, 0, st>>>(fsegs, inconst_ratio_th);
     ZS_LAUNCHED(ctx);
     return ZS_OK;
 }

@@ -72,9 +72,11 @@ constexpr int kStages = 3;
 // launch may span several objects of one cloud size: segment g covers rows [first_row[g], first_row[g+1]).
 constexpr int kMaxFusedSegs = 32;
 struct fused_seg {
-    zs_obj_view o;          // model cloud (global memory; 36 B per point, read coalesced through L1 / L2)
-    const float* poses;     // poses of this segment: row h of the launch is pose h - first_row
-    int first_row, pad_;
+    zs_obj_view o;            // model cloud (global memory; 36 B per point, read coalesced through L1 / L2)
+    const float* poses;       // poses of this segment's object
+    const int32_t* keep_idx;  // kept list of the pre-filter (nullable): hypothesis i of the segment is pose keep_idx[i]
+    const int32_t* n_dev;     // device-side count of the segment (nullable = cap): zs_filter's n_keep_out
+    int first_row, cap;       // first pooled row of the segment (rows are laid out by capacity) and its capacity
 };
 struct fused_args {
     zs_cam cam;
@@ -130,13 +132,38 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
             float* __restrict__ dbg_h2, const int32_t* __restrict__ n_dev, int n_off,
             const __grid_constant__ fused_args fa) {
     constexpr int kThreadsK = kFused ? kThreadsFused : kThreadsTc;
-    n = zs_dyn_count(n_dev, n_off, n);          // zs_set_dynamic_count: the count may live on the device
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Fused: the hypothesis list is the concatenation of the segments' (possibly device-side) counts.  Every warp keeps
+    // the dense first index of segment `lane` in a register: "which segment owns hypothesis h" is one ballot.
+    int seg_first = 0x7fffffff;
+    if (kFused) {
+        int cnt = 0;
+        if (lane < fa.n_seg) {
+            const int32_t* nd = fa.seg[lane].n_dev;
+            cnt = nd ? min(fa.seg[lane].cap, max(0, __ldg(nd))) : fa.seg[lane].cap;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        n = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane < fa.n_seg) seg_first = incl - cnt;
+    } else {
+        n = zs_dyn_count(n_dev, n_off, n);      // zs_set_dynamic_count: the count may live on the device
+    }
+    // (warp-uniform h) -> segment index and index inside the segment
+    auto seg_of = [&](int h, int& local) {
+        const int g = __popc(__ballot_sync(0xffffffffu, seg_first <= h)) - 1;
+        local = h - __shfl_sync(0xffffffffu, seg_first, g);
+        return g;
+    };
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
     auto bar = [&](int i) { return sbase + kSmBar + 8u * (uint32_t)i; };
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cluster_rank();                 // 0 = leader (issues every MMA of the pair)
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const int T = (N + kPairTile - 1) / kPairTile;        // pair-tiles per hypothesis
@@ -203,11 +230,11 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
         for (int i = 0; i < total; ++i) {
             const int s = i % kStages, j = i / T, tt = i - j * T;
             if (tt == 0) {                                      // new hypothesis: its object (segment) and pose
-                const int h = pair + j * n_pairs;
-                int g = 0;
-                while (g + 1 < fa.n_seg && fa.seg[g + 1].first_row <= h) ++g;
+                int local;
+                const int g = seg_of(pair + j * n_pairs, local);
                 pA = fa.seg[g].o.pA; pB = fa.seg[g].o.pB; pV = fa.seg[g].o.pV;
-                P = zs_load_pose(fa.seg[g].poses, h - fa.seg[g].first_row);
+                const int32_t* keep = fa.seg[g].keep_idx;
+                P = zs_load_pose(fa.seg[g].poses, keep ? __ldg(keep + local) : local);
             }
             const int s0 = tt * kPairTile + rank * kTile;
             const int p0 = (s0 + kTile <= N ? s0 : N - kTile) + row0;      // first of this warp's 64 points (N >= kTile)
@@ -400,7 +427,12 @@ zs_k_mlp_tc(const __nv_bfloat16* __restrict__ feat, int n, int N, const uint8_t*
         PROF_DECL;
         for (int i = 0; i < total; ++i) {
             const int j = i / T, tt = i - j * T;
-            const int h = pair + j * n_pairs;
+            int h = pair + j * n_pairs;                                 // pooled row of the hypothesis
+            if (kFused && tt == T - 1) {                                // rows are laid out by segment capacity
+                int local;
+                const int g = seg_of(h, local);
+                h = fa.seg[g].first_row + local;
+            }
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 float qq[4] = {m[cb], -INFINITY, -INFINITY, -INFINITY};
@@ -521,13 +553,14 @@ int zs_score_tc(zs_ctx* ctx, int slot, const __nv_bfloat16* feat, int n, int n_p
 // Fused projection + gather + features + shared MLP + max-pool (bf16): the hypothesis list is the concatenation of the
 // segments (segment i: n_hyp[i] hypotheses of the cloud in obj_slots[i], poses [dev] float32 [n_hyp[i]][12]).
 extern "C" int zs_pool_fused(zs_ctx* ctx, int weight_slot, int n_seg, const int32_t* obj_slots, const float* const* poses,
-                             const int32_t* n_hyp, float* pooled_out, void* stream) {
+                             const int32_t* const* keep_idx, const int32_t* n_hyp, const int32_t* const* n_dev,
+                             float* pooled_out, void* stream) {
     if (!ctx) return ZS_ERR_INVALID;
     if (weight_slot < 0 || weight_slot >= ZS_MAX_WEIGHT_SLOTS || !ctx->w[weight_slot].set)
         return zs_fail(ctx, ZS_ERR_STATE, "weight slot %d not set", weight_slot);
     if (n_seg < 0 || (n_seg > 0 && (!obj_slots || !poses || !n_hyp || !pooled_out)))
         return zs_fail(ctx, ZS_ERR_INVALID, "zs_pool_fused arguments");
-    if (ctx->dyn_n) return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "device-side counts: use zs_features + zs_pool");
+    if (ctx->dyn_n) return zs_fail(ctx, ZS_ERR_UNSUPPORTED, "zs_set_dynamic_count is not used by zs_pool_fused: pass n_dev per segment");
     if (!ctx->frame.set) return zs_fail(ctx, ZS_ERR_STATE, "frame not set");
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     const zs_frame& f = ctx->frame;
@@ -553,7 +586,10 @@ extern "C" int zs_pool_fused(zs_ctx* ctx, int weight_slot, int n_seg, const int3
             fused_seg& g = fa.seg[fa.n_seg++];
             g.o = zs_obj_view{ob.pA, ob.pB, ob.pV, ob.n_pts};
             g.poses = poses[i];
+            g.keep_idx = keep_idx ? keep_idx[i] : nullptr;
+            g.n_dev = n_dev ? n_dev[i] : nullptr;
             g.first_row = n;
+            g.cap = n_hyp[i];
             n += n_hyp[i];
         }
         if (n == 0) continue;

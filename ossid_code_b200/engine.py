@@ -229,6 +229,25 @@ class ZsContext:
                                            float(expand_ratio), mask.data_ptr(), self._stream()), "zs_boxes_to_mask")
         return mask
 
+    def prefilter(self, segments, th: float, mask_th: float = 0.5):
+        """``zs_prefilter``: violations + mask test + compaction for every object of a frame in two launches.
+        ``segments``: ``(slot, poses12, mask or None, viol_out, keep_out, n_keep_out, info_out or None)`` per object
+        (all outputs caller-owned contiguous int32 device views)."""
+        segs = list(segments)
+        n = len(segs)
+        if n == 0:
+            return
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        arr = lambda ctype, vals: (ctype * n)(*vals)
+        has_mask = any(sg[2] is not None for sg in segs)
+        self._ck(self.lib.zs_prefilter(
+            self.h, n, arr(C.c_int32, [sg[0] for sg in segs]), arr(C.c_void_p, [sg[1].data_ptr() for sg in segs]),
+            arr(C.c_int32, [sg[1].shape[0] for sg in segs]),
+            arr(C.c_void_p, [ptr(sg[2]) for sg in segs]) if has_mask else None, float(mask_th), float(th),
+            arr(C.c_void_p, [ptr(sg[3]) for sg in segs]), arr(C.c_void_p, [ptr(sg[4]) for sg in segs]),
+            arr(C.c_void_p, [ptr(sg[5]) for sg in segs]), arr(C.c_void_p, [ptr(sg[6]) for sg in segs]),
+            self._stream()), "zs_prefilter")
+
     def filter(self, viol, n_pts: int, th: float) -> torch.Tensor:
         """Kept hypothesis indices (ascending, int32).  Reads the count back: one 4-byte sync."""
         keep, n_keep = self.filter_async(viol, n_pts, th)
@@ -331,18 +350,26 @@ class ZsContext:
         return pooled
 
     def pool_fused(self, wslot: int, segments, out: torch.Tensor) -> torch.Tensor:
-        """``zs_pool_fused``: featurise + shared MLP + max-pool in one kernel.  ``segments``: [(slot, poses12), ...] of one
-        cloud size; ``out`` (sum of hypotheses, 1024) float32."""
-        segs = [sg for sg in segments if sg[1].shape[0] > 0]
+        """``zs_pool_fused``: featurise + shared MLP + max-pool in one kernel.  ``segments``: ``(slot, poses12)`` or
+        ``(slot, poses12, keep_idx, n_dev)`` per object, all of one cloud size; with ``keep_idx`` (int32 kept list) the
+        segment's capacity is ``len(keep_idx)`` and ``n_dev`` (device int32[1]) says how many of them are live.
+        ``out`` (sum of capacities, 1024) float32."""
+        segs = [tuple(sg) + (None,) * (4 - len(sg)) for sg in segments]
+        segs = [sg for sg in segs if (sg[2] if sg[2] is not None else sg[1]).shape[0] > 0]
         n = len(segs)
         if n == 0:
             return out
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        caps = [(sg[2] if sg[2] is not None else sg[1]).shape[0] for sg in segs]
         slots = (C.c_int32 * n)(*[sg[0] for sg in segs])
         poses = (C.c_void_p * n)(*[sg[1].data_ptr() for sg in segs])
-        counts = (C.c_int32 * n)(*[sg[1].shape[0] for sg in segs])
-        if out.shape[0] < sum(sg[1].shape[0] for sg in segs):
+        keeps = (C.c_void_p * n)(*[ptr(sg[2]) for sg in segs])
+        counts = (C.c_int32 * n)(*caps)
+        ndev = (C.c_void_p * n)(*[ptr(sg[3]) for sg in segs])
+        if out.shape[0] < sum(caps):
             raise ValueError("pool_fused: output has fewer rows than hypotheses")
-        self._ck(self.lib.zs_pool_fused(self.h, wslot, n, slots, poses, counts, out.data_ptr(), self._stream()), "zs_pool_fused")
+        self._ck(self.lib.zs_pool_fused(self.h, wslot, n, slots, poses, keeps, counts, ndev, out.data_ptr(), self._stream()),
+                 "zs_pool_fused")
         return out
 
     def head(self, wslot: int, pooled: torch.Tensor, tensor_cores, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -436,18 +436,21 @@ class FrameScorer:
         #    unfiltered one.
         keeps, n_keeps, n_devs = [], [], []
         filtered = plan.filtered
+        pre = []
         for o, r in enumerate(res):
             keep, n_dev, M = None, None, r["poses12"].shape[0]
             if filtered and M > 0:
                 # the kept list lands in the top-k index map and the kept count in the segment table: no glue kernels
                 a = plan.off[o]
-                viol = ctx.violations(r["slot"], r["poses12"], out=plan.viol[a: a + M], mask=self._masks[o], mask_th=self.mask_th)
-                keep, n_dev = ctx.filter_async(viol, ctx.obj_npts[r["slot"]], self.th, info=info[2 * o: 2 * o + 2],
-                                               keep_out=plan.index_map[a: a + M],
-                                               n_keep_out=plan.seg_dyn.view(-1)[4 * o + 1: 4 * o + 2])
+                keep, n_dev = plan.index_map[a: a + M], plan.seg_dyn.view(-1)[4 * o + 1: 4 * o + 2]
+                pre.append((r["slot"], r["poses12"], self._masks[o], plan.viol[a: a + M], keep, n_dev, info[2 * o: 2 * o + 2]))
             keeps.append(keep)
             n_devs.append(n_dev)
-            n_keeps.append(M if (keep is None or n_dev is not None) else keep.shape[0])     # capacity when the count is on the device
+            n_keeps.append(M)                    # capacity: the live count stays on the device
+        if pre:
+            t = self._mark("prefilter", sum(sg[1].shape[0] for sg in pre))
+            ctx.prefilter(pre, self.th, self.mask_th)       # every object of the frame: one projection pass, one compaction launch
+            self._mark(None, 0, t)
         # 2. row layout: the plan's when nothing was compacted on the host, else recomputed from the kept counts
         order = plan.order
         offs, total = {}, 0
@@ -460,22 +463,30 @@ class FrameScorer:
             cap = max(int(total * 1.25), 1)
             self._pooled = torch.zeros((cap, 1024), dtype=torch.float32, device=ctx.device)
             self._scores = torch.zeros((cap,), dtype=torch.float32, device=ctx.device)
-        # 3. features -> shared MLP + max-pool, chunked so that the feature buffer stays bounded
+        # 3. features -> shared MLP + max-pool
         same_n = len({ctx.obj_npts[r["slot"]] for r in res}) == 1
-        if same_n and all(kp is None for kp in keeps) and total > 0:
-            # no pre-filter, one cloud size: the MLP kernel runs once per chunk of the scorer's concatenated hypothesis
-            # list (several objects per launch) instead of once per object - fewer launch prologues and a last wave of
-            # CTA pairs that is 1/443 instead of 1/136 of the launch
-            N = ctx.obj_npts[res[0]["slot"]]
+        N0 = ctx.obj_npts[res[0]["slot"]] if res else 0
+        if self.fused and same_n and N0 >= 128 and total > 0:
+            # bf16 path, one cloud size: projection + gather + features + MLP + max-pool of a scorer's whole hypothesis
+            # list in ONE kernel (zs_pool_fused); with a pre-filter every object's kept list and device-side count go in
+            # as they are (rows stay laid out by capacity), so a filtered frame takes the same single launch per scorer
             for ws in sorted({res[o]["wslot"] for o in order}):
                 members = [o for o in order if res[o]["wslot"] == ws]
                 lo, hi = offs[members[0]], offs[members[-1]] + n_keeps[members[-1]]
-                if self.fused and N >= 128:
-                    # projection + gather + features + MLP + max-pool of the scorer's whole hypothesis list in one kernel
-                    t = self._mark("pool", (hi - lo) * N)
-                    ctx.pool_fused(ws, [(res[o]["slot"], res[o]["poses12"]) for o in members], out=self._pooled[lo:hi])
+                if hi > lo:
+                    t = self._mark("pool", (hi - lo) * N0)
+                    ctx.pool_fused(ws, [(res[o]["slot"], res[o]["poses12"], keeps[o], n_devs[o]) for o in members
+                                        if n_keeps[o] > 0], out=self._pooled[lo:hi])
                     self._mark(None, 0, t)
-                    continue
+            order_for_loop = []
+        elif same_n and all(kp is None for kp in keeps) and total > 0:
+            # no pre-filter, one cloud size, two-kernel path (fused=False or the fp32-accurate scorer): the MLP kernel runs
+            # once per chunk of the scorer's concatenated hypothesis list (several objects per launch), chunked so that
+            # the feature buffer stays bounded
+            N = N0
+            for ws in sorted({res[o]["wslot"] for o in order}):
+                members = [o for o in order if res[o]["wslot"] == ws]
+                lo, hi = offs[members[0]], offs[members[-1]] + n_keeps[members[-1]]
                 for cs in range(lo, hi, self.chunk):
                     ce = min(cs + self.chunk, hi)
                     feat = self._feat_buf(ce - cs, N, min(self.chunk, hi - lo))

@@ -396,14 +396,47 @@ def test_fused_features_and_mlp_equal_the_two_kernel_sequence(ctx, n_pts, n_obj,
     assert bool((out[n_obj * n_hypo:] == -7.0).all()), "rows beyond the hypothesis list were written"
 
 
-def test_frame_scorer_fused_equals_unfused(ctx):
+def test_fused_kernel_with_kept_lists_and_device_counts(ctx):
+    """zs_pool_fused with a pre-filter's outputs: per segment a kept-index list and a device-side count (one segment
+    empty, one full, one partial); rows are laid out by capacity and rows beyond a count stay untouched."""
+    from ossid_code_b200.engine import poses_to_rt12
+    sc = syn.make_scene(67, "lmo", n_obj=3, n_pts=384, n_hypo=120)
+    ctx.set_frame_u8(sc["img"], sc["depth"], glue.K2meta(sc["cam_K"]))
+    ctx.set_weights(1, weights.seeded_folded(3))
+    g = torch.Generator().manual_seed(1)
+    segs, ref_rows = [], []
+    out = torch.full((3 * 120, 1024), -7.0, device=ctx.device)
+    for s, (ob, live) in enumerate(zip(sc["objects"], (37, 0, 120))):
+        ctx.set_object(s, ob["model_points"], ob["model_colors"], ob["model_normals"])
+        p12 = poses_to_rt12(ob["pose_hypos"], ctx.device)
+        keep = torch.randperm(120, generator=g).to(torch.int32).to(ctx.device)
+        n_dev = torch.tensor([live], dtype=torch.int32, device=ctx.device)
+        segs.append((s, p12, keep, n_dev))
+        feat, _, _, _ = ctx.features(s, p12, keep_idx=keep[:live].contiguous(), dtype=torch.bfloat16) if live else (None,) * 4
+        ref_rows.append(ctx.pool(1, feat) if live else None)
+    ctx.pool_fused(1, segs, out=out)
+    for s, (ref, live) in enumerate(zip(ref_rows, (37, 0, 120))):
+        rows = out[s * 120: (s + 1) * 120]
+        if live:
+            assert torch.equal(rows[:live], ref), f"segment {s}"
+        assert bool((rows[live:] == -7.0).all()), f"segment {s}: rows beyond the device-side count were written"
+
+
+@pytest.mark.parametrize("th,boxes", [(100.0, False), (10.0, False), (100.0, True), (10.0, True)])
+def test_frame_scorer_fused_equals_unfused(ctx, th, boxes):
+    """FrameScorer with the fused kernel == the two-kernel sequence, bit for bit: unfiltered, free-space pre-filter,
+    detection boxes, both."""
     sc = syn.make_scene(59, "ycbv", n_obj=5, n_pts=1000, n_hypo=400)
+    if boxes:
+        for ob in sc["objects"]:
+            ob["boxes"], ob["box_scores"] = np.asarray([syn.gt_box(sc, ob, 1.0)], dtype=np.float64), np.asarray([0.9])
     ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
     res = []
     for fused in (True, False):
-        fs = scoring.FrameScorer(ws, device=0, precision="bf16", k=8, fused=fused, rerank=False)
-        res.append(fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=lambda o: o % 2))
-    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+        fs = scoring.FrameScorer(ws, device=0, precision="bf16", k=8, fused=fused, rerank=False, inconst_ratio_th=th)
+        res.append(fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=lambda o: o % 2) + (fs.last_scored,))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]
+    assert (th >= 100 and not boxes) == (res[0][2] == 2000)
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
@@ -444,6 +477,38 @@ def test_frame_scorer_with_detection_boxes_equals_oracle_pipeline(ctx, precision
     assert fs.last_scored == n_scored and (I[2] < 0).all() and 0 < n_scored < 900
     Sm, Im, _ = _emulate_ranks(fs, sc, 3, wof)
     assert np.array_equal(Im, I) and np.array_equal(Sm, S)
+
+
+def test_prefilter_of_a_whole_frame_equals_per_object_calls(ctx):
+    """zs_prefilter (two launches for all objects) == zs_violations + zs_filter object by object: different cloud sizes,
+    one object with a detection mask, one whose hypotheses are all rejected, 40 objects (two projection launches)."""
+    from ossid_code_b200.engine import poses_to_rt12
+    sc = syn.make_scene(79, "lmo", n_obj=3, n_pts=500, n_hypo=333)
+    for key in ("model_points", "model_colors", "model_normals"):
+        sc["objects"][1][key] = sc["objects"][1][key][:130].copy()
+    far = np.tile(np.eye(4), (333, 1, 1)); far[:, 2, 3] = 0.05
+    sc["objects"][2]["pose_hypos"] = far
+    ctx.set_frame_u8(sc["img"], sc["depth"], glue.K2meta(sc["cam_K"]))
+    x1, y1, x2, y2 = syn.gt_box(sc, sc["objects"][0], 1.2)
+    mask = torch.zeros((sc["H"], sc["W"]), dtype=torch.uint8, device=ctx.device)
+    mask[y1:y2, x1:x2] = 1
+    segs, refs = [], []
+    for s in range(40):
+        ob = sc["objects"][s % 3]
+        ctx.set_object(s, ob["model_points"], ob["model_colors"], ob["model_normals"])
+        p12 = poses_to_rt12(np.roll(ob["pose_hypos"], s, axis=0), ctx.device)
+        m = mask if s % 3 == 0 else None
+        viol = ctx.violations(s, p12, mask=m, mask_th=0.5)
+        keep, n_keep = ctx.filter_async(viol, ctx.obj_npts[s], 10.0, info=(info := torch.zeros(2, dtype=torch.int32, device=ctx.device)))
+        refs.append((viol, keep, n_keep, info))
+        dev = lambda n: torch.full((n,), -3, dtype=torch.int32, device=ctx.device)
+        segs.append((s, p12, m, dev(333), dev(333), dev(1), dev(2)))
+    ctx.prefilter(segs, 10.0, 0.5)
+    for s, (sg, (viol, keep, n_keep, info)) in enumerate(zip(segs, refs)):
+        nk = int(n_keep)
+        assert torch.equal(sg[3], viol) and int(sg[5]) == nk and torch.equal(sg[4][:nk], keep[:nk]) and torch.equal(sg[6], info), s
+    assert int(segs[2][5]) == 1 and int(segs[2][6][0]) == 0, "all rejected: the never-empty rule keeps one"
+    assert 0 < int(segs[0][5]) < 333 and bool((segs[0][3] == 0x7fffffff).any())
 
 
 def test_more_objects_than_cloud_slots_raises(ctx):
