@@ -410,6 +410,14 @@ def main():
     ms_total = max_over_ranks(ms)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
+    # the same K steps replayed from a CUDA graph (single GPU; what score_frames does): no per-stage events inside, so
+    # it is reported beside `value`, whose timed region carries the events the roofline numbers come from
+    graph_ms = None
+    if world == 1 and fs.use_graph:
+        run.resident(3 * n_frames)
+        graph_ms = run.resident(args.steps * n_frames)[0] / args.steps
+        if not fs._graphs:
+            graph_ms = None
     value = total_hyp / (ms_step * 1e-3)
     scored = int(fs.last_scored) * n_frames if fs._plan.filtered else total_hyp
 
@@ -529,6 +537,9 @@ def main():
                 "vs_resident": e2e_s * 1e3 / ms_step},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if graph_ms is not None:
+        line["cuda_graph"] = {"ms_per_step": graph_ms, "value": total_hyp / (graph_ms * 1e-3),
+                              "note": "the step replayed from a CUDA graph (FrameScorer's default on one GPU, used by the e2e arm)"}
     line.update(roof)
 
     # ---- strong scaling of fixed frames + on-hardware identity of the sharded result (N > 1) --------

@@ -76,6 +76,11 @@ ZS_API void zs_destroy(zs_ctx* ctx);
 ZS_API const char* zs_last_error(const zs_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 ZS_API int64_t zs_launch_count(const zs_ctx* ctx);
+/* Changes whenever something a recorded launch sequence depends on has changed inside the context: a context-owned
+ * buffer moved (bigger frame, bigger cloud, grown scratch) or a launch parameter kept by the context changed (frame
+ * size, intrinsics, a slot's point count).  A caller that replays captured launches (CUDA graph) re-captures when it
+ * differs from the value at capture time. */
+ZS_API int64_t zs_alloc_generation(const zs_ctx* ctx);
 
 /* Sizes the context's scratch for scoring calls of up to max_hypotheses hypotheses, so that no later call allocates
  * or frees device memory between the kernels of a frame (allocation synchronises the device).  Optional: without

@@ -21,6 +21,7 @@ SIGNATURES = {
     "zs_destroy": (None, [_p]),
     "zs_last_error": (C.c_char_p, [_p]),
     "zs_launch_count": (C.c_int64, [_p]),
+    "zs_alloc_generation": (C.c_int64, [_p]),
     "zs_set_frame": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _f, _f, _p]),
     "zs_set_frame_u8": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _f, _f, _i, _p]),
     "zs_set_object": (_i, [_p, _i, _p, _p, _p, _i, _p]),

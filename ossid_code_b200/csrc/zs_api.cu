@@ -18,6 +18,7 @@ int zs_reserve_ws(zs_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->ws_bytes) return ZS_OK;
     // Grow-only scratch; cudaFree synchronises the device, which orders it after pending users.  Steady-state callers
     // size it once up front with zs_reserve() so that no allocation happens between the kernels of a frame.
+    ctx->alloc_gen++;
     if (ctx->ws) ZS_CUDA(ctx, cudaFree(ctx->ws));
     ctx->ws = nullptr;
     ctx->ws_bytes = 0;
@@ -117,6 +118,7 @@ extern "C" void zs_destroy(zs_ctx* ctx) {
 
 extern "C" const char* zs_last_error(const zs_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" int64_t zs_launch_count(const zs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t zs_alloc_generation(const zs_ctx* ctx) { return ctx ? ctx->alloc_gen : 0; }
 
 // ---------------------------------------------------------------------------------------
 // Frame packing: {depth/camera_scale, H, S, V} per pixel (one 16-byte gather per projected point).
@@ -175,6 +177,7 @@ static int zs_frame_common(zs_ctx* ctx, int H, int W, float fx, float fy, float 
     size_t n_px = (size_t)H * W;
     if (n_px > ctx->frame.cap_px) {
         ctx->frame.set = false;             // stays unset if the regrow fails (zs_features then reports ZS_ERR_STATE)
+        ctx->alloc_gen++;
         ZS_CUDA(ctx, cudaFree(ctx->frame.packed));
         ctx->frame.packed = nullptr;
         ctx->frame.cap_px = 0;
@@ -184,6 +187,9 @@ static int zs_frame_common(zs_ctx* ctx, int H, int W, float fx, float fy, float 
         }
         ctx->frame.cap_px = n_px;
     }
+    if (ctx->frame.H != H || ctx->frame.W != W || ctx->frame.fx != fx || ctx->frame.fy != fy || ctx->frame.cx != cx ||
+        ctx->frame.cy != cy)
+        ctx->alloc_gen++;                        // captured launches carry the camera as a parameter
     ctx->frame.H = H; ctx->frame.W = W;
     ctx->frame.fx = fx; ctx->frame.fy = fy; ctx->frame.cx = cx; ctx->frame.cy = cy;
     ctx->frame.inv_fx = 1.0f / fx;      // fp32 reciprocal, as the oracle computes it
@@ -244,6 +250,7 @@ extern "C" int zs_set_object(zs_ctx* ctx, int slot, const float* pts, const floa
     ZS_CUDA(ctx, cudaSetDevice(ctx->device));
     zs_object& o = ctx->obj[slot];
     if (n_pts > o.cap) {
+        ctx->alloc_gen++;
         ZS_CUDA(ctx, cudaFree(o.pA)); ZS_CUDA(ctx, cudaFree(o.pB)); ZS_CUDA(ctx, cudaFree(o.pV));
         o.pA = o.pB = nullptr; o.pV = nullptr; o.cap = 0; o.n_pts = 0;
         if (cudaMalloc(&o.pA, n_pts * sizeof(float4)) != cudaSuccess ||
@@ -256,6 +263,7 @@ extern "C" int zs_set_object(zs_ctx* ctx, int slot, const float* pts, const floa
     }
     zs_k_pack_object<<<(n_pts + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, cols, nrms, o.pA, o.pB, o.pV, n_pts);
     ZS_LAUNCHED(ctx);
+    if (o.n_pts != n_pts) ctx->alloc_gen++;      // captured launches carry the point count as a parameter
     o.n_pts = n_pts;
     return ZS_OK;
 }

@@ -46,6 +46,7 @@ struct zs_ctx {
     int device = 0;
     int sm_count = 148;
     int64_t launches = 0;
+    int64_t alloc_gen = 0;           // bumped whenever a context-owned device buffer moves (frame, cloud, scratch)
     char err[512] = {0};
     zs_frame frame;
     zs_object obj[ZS_MAX_OBJECTS];

@@ -82,6 +82,7 @@ class ZsContext:
         self.frame_hw = None
         self.obj_npts = {}
         self.weight_owner = {}        # slot -> token of whoever uploaded last (see set_weights)
+        self.graph_launches = 0       # kernels executed by CUDA-graph replays (FrameScorer), not seen by zs_launch_count
 
     def close(self):
         if getattr(self, "h", None):
@@ -103,7 +104,13 @@ class ZsContext:
 
     @property
     def launches(self) -> int:
-        return int(self.lib.zs_launch_count(self.h))
+        """Kernels launched through this context: the library's count plus the kernels of replayed CUDA graphs."""
+        return int(self.lib.zs_launch_count(self.h)) + self.graph_launches
+
+    @property
+    def generation(self) -> int:
+        """``zs_alloc_generation``: changes when a replayed launch sequence would no longer be valid."""
+        return int(self.lib.zs_alloc_generation(self.h))
 
     # -- uploads ----------------------------------------------------------------------
     def set_frame(self, img01, depth, meta):

@@ -171,7 +171,7 @@ class FrameScorer:
     def __init__(self, weights: Sequence[dict], device: Optional[int] = None, precision: str = "bf16",
                  inconst_ratio_th: float = 100.0, k: int = 8, chunk: int = 32768, group=None,
                  ctx: Optional[ZsContext] = None, reorder_points: bool = True, rerank: Optional[bool] = None,
-                 fused: bool = True, mask_th: float = 0.5):
+                 fused: bool = True, mask_th: float = 0.5, graph: bool = True):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         if len(weights) > MAX_WEIGHT_SLOTS:
@@ -187,6 +187,12 @@ class FrameScorer:
         # bf16 path without pre-filter: features are computed inside the MLP kernel (zs_pool_fused) instead of being
         # written to HBM by zs_features and read back; fused=False keeps the two-kernel sequence (bit-identical results)
         self.fused = bool(fused) and precision == "bf16"
+        # single-GPU steps are replayed from a CUDA graph after their first two runs (one eager warm-up, one capture): a
+        # frame is 15-40 launches, and for a frame of a few thousand hypotheses (the reference's own call size) issuing
+        # them from Python costs more than running them.  Same kernels, same buffers, same results.
+        self.use_graph = bool(graph)
+        self._graphs, self._graph_warm_gen = {}, {}
+        self._buf_gen = 0                 # bumped whenever a FrameScorer-owned device buffer is (re)allocated
         self._weights = list(weights)
         self._wtoken = [object() for _ in weights]       # ownership tokens of this scorer's weight slots
         self.n_weights = len(weights)
@@ -396,6 +402,7 @@ class FrameScorer:
             if "mask" in ob or "boxes" in ob:
                 if self._mask_dev is None or self._mask_dev.shape[0] < len(objects) or self._mask_dev.shape[1:] != tuple(ctx.frame_hw):
                     self._mask_dev = torch.zeros((len(objects),) + tuple(ctx.frame_hw), dtype=torch.uint8, device=ctx.device)
+                    self._buf_gen += 1
                 m = self._mask_dev[o]
                 if "mask" in ob:
                     m.copy_((torch.as_tensor(ob["mask"]) != 0).to(torch.uint8), non_blocking=True)
@@ -407,6 +414,7 @@ class FrameScorer:
         p12 = self._p12[buf]
         if p12 is None or p12.shape[0] < plan.total:
             p12 = self._p12[buf] = torch.empty((max(int(plan.total * 1.25), 1), 12), dtype=torch.float32, device=ctx.device)
+            self._buf_gen += 1
         ctx.pack_poses(self._raw[buf][: plan.total], out=p12)
         done = torch.cuda.Event()
         done.record(stream)
@@ -423,6 +431,44 @@ class FrameScorer:
         """Featurise + score + top-k for the uploaded frame.  Returns (scores (n_obj,k), index (n_obj,k))
         tensors on the device; indices are global hypothesis indices per object, -1 = empty slot.
         ``local_record=True`` (tests that emulate ranks on one device) returns this rank's candidate record instead."""
+        rank, world = self._rank_world()
+        if not self.use_graph or local_record or self.stage_events is not None or world > 1 or self.forced_rank_world:
+            return self._run_resident(local_record)
+        # the launch sequence only depends on the plan (shapes) and on which pose buffer the upload used
+        key = (id(self._plan), self._buf)
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._sync_weights()
+            gens = (self._buf_gen, self.ctx.generation)
+            if self._graph_warm_gen.get(key) != gens:     # first run: eager (sizes every buffer, loads every kernel)
+                out = self._run_resident(False)
+                self._graph_warm_gen[key] = (self._buf_gen, self.ctx.generation)
+                return out
+            try:
+                l0 = self.ctx.launches
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    S, I = self._run_resident(False)
+                entry = self._graphs[key] = (g, S, I, self._result_flat, self._scored, self.ctx.launches - l0,
+                                             (self._buf_gen, self.ctx.generation))
+            except Exception as exc:                      # capture refused: keep launching eagerly
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the scoring step failed ({exc}); launching kernel by kernel")
+                self.use_graph = False
+                torch.cuda.synchronize(self.ctx.device)
+                return self._run_resident(False)
+        g, S, I, flat, scored, n_launch, gens = entry
+        if gens != (self._buf_gen, self.ctx.generation):  # a buffer the recorded launches point at has moved: re-capture
+            del self._graphs[key]
+            self._graph_warm_gen.pop(key, None)
+            return self.run_resident()
+        self._sync_weights()                              # (re-)uploads go into the same buffers the graph reads
+        g.replay()
+        self.ctx.graph_launches += n_launch
+        self._result_flat, self._scored = flat, scored
+        return S, I
+
+    def _run_resident(self, local_record: bool = False):
         ctx, k = self.ctx, self.k
         res, plan = self._resident, self._plan
         n_obj, nk = plan.n_obj, plan.n_obj * k
@@ -463,6 +509,7 @@ class FrameScorer:
             cap = max(int(total * 1.25), 1)
             self._pooled = torch.zeros((cap, 1024), dtype=torch.float32, device=ctx.device)
             self._scores = torch.zeros((cap,), dtype=torch.float32, device=ctx.device)
+            self._buf_gen += 1
         # 3. features -> shared MLP + max-pool
         same_n = len({ctx.obj_npts[r["slot"]] for r in res}) == 1
         N0 = ctx.obj_npts[res[0]["slot"]] if res else 0
@@ -573,6 +620,7 @@ class FrameScorer:
         need = rows * per
         if self._feat is None or self._feat.numel() < need:
             self._feat = torch.empty((max(need, rows_cap * per),), dtype=torch.bfloat16, device=self.ctx.device)
+            self._buf_gen += 1
         return self._feat[:need].view(rows, 2, N, 8) if self.split else self._feat[:need].view(rows, N, 8)
 
     def _rerank(self, S, I, P):
@@ -585,6 +633,7 @@ class FrameScorer:
         Nmax = max(ctx.obj_npts[o] for o in range(n_obj))
         if rr is None or rr["rows"] < n_obj * k or rr["N"] < Nmax:
             rows = n_obj * k
+            self._buf_gen += 1
             rr = self._rr = dict(rows=rows, N=Nmax,
                                  feat=torch.zeros((rows * Nmax * 16,), dtype=torch.bfloat16, device=ctx.device),
                                  pooled=torch.zeros((rows, 1024), dtype=torch.float32, device=ctx.device),

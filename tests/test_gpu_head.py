@@ -511,6 +511,36 @@ def test_prefilter_of_a_whole_frame_equals_per_object_calls(ctx):
     assert 0 < int(segs[0][5]) < 333 and bool((segs[0][3] == 0x7fffffff).any())
 
 
+@pytest.mark.parametrize("th", [100.0, 10.0])
+def test_cuda_graph_replay_equals_eager_launches(ctx, th):
+    """After one eager run and one capture a single-GPU step is replayed from a CUDA graph; different frames of the same
+    shape (new image, depth, poses), a frame of another shape in between, a bigger cloud (context buffers move) and a
+    second user of the context's weight slots must all give exactly what the kernel-by-kernel scorer gives."""
+    from ossid_code_b200 import zephyr_shim
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    wof = lambda o: o % 2
+    fg = scoring.FrameScorer(ws, device=0, precision="bf16", k=6, inconst_ratio_th=th, graph=True)
+    fe = scoring.FrameScorer(ws, device=0, precision="bf16", k=6, inconst_ratio_th=th, graph=False)
+    frames = [syn.make_scene(seed, "lmo", n_obj=3, n_pts=256, n_hypo=200) for seed in (83, 84, 85, 86, 87)]
+    other = syn.make_scene(88, "lmo", n_obj=2, n_pts=256, n_hypo=90)
+    bigger = syn.make_scene(89, "lmo", n_obj=3, n_pts=700, n_hypo=200)
+    seq = frames[:3] + [other] + frames[3:] + frames + [bigger, frames[0], bigger, bigger, frames[1], bigger, bigger]
+    l0 = fg.ctx.launches
+    for i, sc in enumerate(seq):
+        Sg, Ig = fg.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=wof)
+        Se, Ie = fe.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=wof)
+        assert np.array_equal(Sg, Se) and np.array_equal(Ig, Ie), f"frame {i}"
+        if i == 6:                                            # another user takes the context's weight slots
+            m = zephyr_shim.PointNet2SSG(8, None, 1)
+            m.load_state_dict(weights.seeded_state_dict(9))
+            m.to(0).eval()({"point_x": torch.zeros(2, 64, 8, device=ctx.device)})
+    assert fg.use_graph and fg.ctx.graph_launches > 0 and fg.ctx.launches > l0, "the step was never replayed from a graph"
+    out = fg.score_frames([dict(img=sc["img"], depth=sc["depth"], cam_K=sc["cam_K"], objects=sc["objects"]) for sc in frames], wof)
+    for sc, (S, I) in zip(frames, out):
+        Se, Ie = fe.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=wof)
+        assert np.array_equal(S, Se) and np.array_equal(I, Ie)
+
+
 def test_more_objects_than_cloud_slots_raises(ctx):
     sc = syn.make_scene(19, "tiny", n_obj=1, n_pts=32, n_hypo=4)
     fs = scoring.FrameScorer([weights.seeded_folded(0)], device=0, k=2)
