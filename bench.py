@@ -518,6 +518,13 @@ def main():
                         roof[key]["traffic"] = tr[stage]["dram_read_bytes"] + tr[stage]["dram_write_bytes"]
                         roof[key]["traffic_source"] = f"profiles/{tname} (ncu --set full, bytes of the first captured launch: 10,000 hypotheses for the feature kernel, a 32,768-hypothesis chunk for the MLP kernel)"
             break
+    if "roofline" in roof and "pool" in stages:
+        # HBM side of the dominant kernel (it is tensor-bound; this is what `traffic` is to be compared with): fused = pose in,
+        # pooled vector out; two-kernel path = feature rows in, pooled vector out
+        hyp_per_launch = stages["pool"]["units"] / n_pts / stages["pool"]["calls"]
+        per_hyp = (48 + 4096) if "features" not in stages else (n_pts * 8 * fbytes + 4096)
+        roof["roofline"]["algorithmic_hbm_bytes_per_launch"] = per_hyp * hyp_per_launch
+        roof["roofline"]["hypotheses_per_launch"] = hyp_per_launch
     if "roofline_features" in roof:
         roof["roofline_features"]["algorithmic_bytes_per_launch"] = \
             (48 + n_pts * 8 * fbytes) * stages["features"]["units"] / n_pts / stages["features"]["calls"]
