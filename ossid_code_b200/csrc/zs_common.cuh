@@ -11,7 +11,7 @@
 
 #include "../../include/zs.h"
 
-#define ZS_SCORE_CHUNK 32768    // hypotheses per scoring chunk (bounds the head's workspace)
+#define ZS_SCORE_CHUNK 131072   // hypotheses per scoring chunk (bounds the head's workspace: 13 KB per hypothesis)
 // scratch floats per hypothesis of a chunk: pooled 1024 | g1 512 | g2 256 | lo(pooled) 1024 | lo(g1) 512
 #define ZS_HEAD_WS_FLOATS (1024 + 512 + 256 + 1024 + 512)
 #define ZS_VIOL_MASKED 0x7fffffff   // zs_violations: the hypothesis failed the mask-overlap test (zs_filter never keeps it)

@@ -4,9 +4,10 @@
 //
 // One generic kernel, out[n][CO] = relu(A[n][K] . W[CO][K]^T + b), kind::tf32 (fp32 operands read
 // straight from the fp32 buffers, 10-bit mantissa in the multiplier, fp32 accumulate in TMEM):
-//   * CTA tile 128 rows x 256 output channels, K walked in blocks of 32 floats (= one 128-byte
-//     swizzle row); A and W tiles arrive by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) through a
-//     4-stage mbarrier ring; 4 MMAs (M=128, N=256, K=8) per block issued by one thread.
+//   * CTA tile 256 rows x 256 output channels (two 128-row accumulators = all 512 TMEM columns), K walked in
+//     blocks of 32 floats (= one 128-byte swizzle row); A and W tiles arrive by TMA (cp.async.bulk.tensor.2d,
+//     SWIZZLE_128B) through a 3-stage mbarrier ring of 64 KB stages; 8 MMAs (M=128, N=256, K=8) per block
+//     issued by one thread.  With kTerms = 3 the K loop runs three times (hi.hi + lo.hi + hi.lo): fp32-accurate.
 //   * warps: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-5 = epilogue (thread = row).
 //   * fc2's epilogue folds fc3 in: each thread owns all 256 hidden values of its hypothesis and
 //     reduces them against F3 in registers, so only one float per hypothesis is written.
@@ -18,11 +19,14 @@
 namespace {
 
 constexpr int kThreadsFc = 192;
-constexpr int kFcStages = 4;
-constexpr int kBM = 128, kBN = 256, kBK = 32;                 // rows, output channels, floats per k-block
-constexpr uint32_t kStageA = kBM * kBK * 4;                   // 16 KB
+constexpr int kFcStages = 3;
+// CTA tile = 256 rows x 256 output channels as TWO 128-row MMAs per K step (two 256-column accumulators, all 512 TMEM
+// columns): per K-block a CTA pulls 32 KB of A + 32 KB of W for 8 MMAs instead of 16 + 32 KB for 4.  fc1 is bound by
+// L2 -> shared-memory traffic (every CTA streams all of F1), so a third less traffic per MMA is a third less time.
+constexpr int kBM = 256, kMmaM = 128, kBN = 256, kBK = 32;    // rows, rows per MMA, output channels, floats per k-block
+constexpr uint32_t kStageA = kBM * kBK * 4;                   // 32 KB
 constexpr uint32_t kStageW = kBN * kBK * 4;                   // 32 KB
-constexpr uint32_t kStageBytes = kStageA + kStageW;           // 48 KB
+constexpr uint32_t kStageBytes = kStageA + kStageW;           // 64 KB
 constexpr uint32_t kFcBar = kFcStages * kStageBytes;          // barriers after the ring
 constexpr uint32_t kFcTmemPtr = kFcBar + 128;
 constexpr uint32_t kFcSmAlloc = kFcTmemPtr + 16 + 1024;
@@ -114,7 +118,7 @@ zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kFcTmemPtr), "r"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kFcTmemPtr), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -135,7 +139,7 @@ zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(kBM, kBN);
+            constexpr uint32_t idesc = make_idesc_tf32(kMmaM, kBN);
             for (int kb = 0; kb < n_kb; ++kb) {
                 const int s = kb % kFcStages;
                 mbar_wait(full(s), (kb / kFcStages) & 1);
@@ -143,8 +147,10 @@ zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {              // 4 x (K = 8 floats = 32 bytes)
                     const uint64_t da = make_desc_sw128(sbase + s * kStageBytes + kk * 32);
+                    const uint64_t da2 = make_desc_sw128(sbase + s * kStageBytes + kMmaM * kBK * 4 + kk * 32);   // rows 128-255
                     const uint64_t db = make_desc_sw128(sbase + s * kStageBytes + kStageA + kk * 32);
                     tc_mma_tf32(tmem, da, db, idesc, (kb | kk) != 0);
+                    tc_mma_tf32(tmem + kBN, da2, db, idesc, (kb | kk) != 0);
                 }
                 tc_commit(empty(s));
             }
@@ -152,10 +158,12 @@ zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         }
     } else {
         const int q = warp & 3;                               // TMEM lane quadrant this warp may read
-        const int row = row0 + q * 32 + lane;
-        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         mbar_wait(acc_full, 0);
         tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < kBM / kMmaM; ++half) {        // accumulator of rows [0,128) then of rows [128,256)
+        const int row = row0 + half * kMmaM + q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + half * kBN;
         float dot = 0.f;
 #pragma unroll 1
         for (int g = 0; g < kBN / 64; ++g) {
@@ -187,6 +195,7 @@ zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             }
         }
         if (kFuseOut && row < n) out[row] = dot + __ldg(c3);
+      }
     }
 
     tc_fence_before();
@@ -194,7 +203,7 @@ zs_k_fc_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
 }
 
