@@ -24,7 +24,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from .engine import POSE_DTYPES, ZsContext, get_context, poses_to_rt12
+from .engine import ZsContext, get_context, poses_to_rt12
 
 MAX_OBJECTS = 64          # ZS_MAX_OBJECTS (include/zs.h): model-cloud slots per context
 MAX_WEIGHT_SLOTS = 4      # ZS_MAX_WEIGHT_SLOTS
@@ -497,7 +497,7 @@ class FrameScorer:
             t = self._mark("prefilter", sum(sg[1].shape[0] for sg in pre))
             ctx.prefilter(pre, self.th, self.mask_th)       # every object of the frame: one projection pass, one compaction launch
             self._mark(None, 0, t)
-        # 2. row layout: the plan's when nothing was compacted on the host, else recomputed from the kept counts
+        # 2. row layout (by capacity: the plan's)
         order = plan.order
         offs, total = {}, 0
         for o in order:
@@ -696,7 +696,12 @@ class FrameScorer:
 
     # -- public end-to-end call -------------------------------------------------------------
     def score_frame(self, img_u8, depth, cam_K, objects: List[dict], weight_of=lambda o: 0):
-        """Host buffers in, host results out: ``(scores (n_obj,k), indices (n_obj,k))`` numpy arrays."""
+        """Host buffers in, host results out: ``(scores (n_obj,k), indices (n_obj,k))`` numpy arrays.  A frame with more
+        objects than the context has cloud slots (64) is scored in groups of 64."""
+        if len(objects) > MAX_OBJECTS:
+            parts = [self.score_frame(img_u8, depth, cam_K, objects[g: g + MAX_OBJECTS], lambda o, g=g: weight_of(g + o))
+                     for g in range(0, len(objects), MAX_OBJECTS)]
+            return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
         self.upload(img_u8, depth, cam_K, objects, weight_of)
         S, I = self.run_resident()
         return S.cpu().numpy(), I.cpu().numpy()

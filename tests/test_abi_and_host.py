@@ -201,3 +201,9 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"].startswith("c2")
+    # both arms print the same `config` object (the driver's same_config check)
+    sys.path.insert(0, root)
+    import argparse
+    import bench
+    ns = argparse.Namespace(workload="c2", k=8, inconst_th=100.0, precision="bf16", no_fuse=False)
+    assert d["config"] == bench.config_for(ns, 1, "weak")

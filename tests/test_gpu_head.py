@@ -546,6 +546,12 @@ def test_more_objects_than_cloud_slots_raises(ctx):
     fs = scoring.FrameScorer([weights.seeded_folded(0)], device=0, k=2)
     with pytest.raises(ValueError, match="at most 64 objects"):
         fs.upload(sc["img"], sc["depth"], sc["cam_K"], [sc["objects"][0]] * 65)
+    # the host-buffer API scores such a frame in groups of 64 instead
+    objs = [dict(sc["objects"][0], pose_hypos=np.roll(sc["objects"][0]["pose_hypos"], o, axis=0)) for o in range(70)]
+    S, I = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], objs)
+    S0, I0 = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], objs[:1])
+    assert S.shape == (70, 2) and np.array_equal(S[0], S0[0]) and np.array_equal(I[0], I0[0])
+    assert all(np.array_equal(S[o], S[0]) and np.array_equal((I[o] - o) % 4, I[0]) for o in range(70))
 
 
 @pytest.mark.parametrize("chunk", [96, 32768])
