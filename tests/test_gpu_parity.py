@@ -309,6 +309,42 @@ def test_full_c2_frame_top1_is_the_fp32_argmax(ctx):
         assert all(S[o, j] >= S[o, j + 1] for j in range(7))
 
 
+@pytest.mark.parametrize("intr,n_obj,n_hypo,n_pts", [("lmo", 8, 50000, 1000), ("hd", 1, 200000, 4000)])
+def test_full_c3_c4_frames_top1_is_the_fp32_argmax(ctx, intr, n_obj, n_hypo, n_pts):
+    """BASELINE.json configs[2] and [3] at full size (8 objects x 50,000 hypotheses x 1,000 points; 1280x720, 200,000
+    hypotheses x 4,000 points): the reported top-1 of every object is the fp32 oracle's argmax over the GPU's candidates
+    plus 128 random hypotheses, unconditionally; also checked with the frame sharded over 4 emulated ranks."""
+    import cv2
+    sc = syn.make_scene(2, intr, n_obj=n_obj, n_pts=n_pts, n_hypo=10000)
+    rng = np.random.default_rng(9)
+    for ob in sc["objects"]:
+        extra = [syn.make_hypotheses(rng, ob["gt_pose"], 10000, sc["cam_K"], sc["H"], sc["W"]) for _ in range(n_hypo // 10000 - 1)]
+        ob["pose_hypos"] = np.concatenate([ob["pose_hypos"], *extra])
+    ws = [weights.seeded_folded(0), weights.seeded_folded(1)]
+    wof = lambda o: o % 2
+    fs = scoring.FrameScorer(ws, device=0, precision="bf16", k=8)
+    S, I = fs.score_frame(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], weight_of=wof)
+    img01 = cv2.GaussianBlur(sc["img"], (5, 5), 0) / 255.
+    meta = glue.K2meta(sc["cam_K"])
+    for o, ob in enumerate(sc["objects"]):
+        cand = sorted(set(int(i) for i in I[o] if i >= 0) | set(rng.choice(n_hypo, 128, replace=False).tolist()))
+        f = zo.features(img01, sc["depth"], ob["pose_hypos"][cand], meta, ob["model_points"], ob["model_colors"],
+                        ob["model_normals"])
+        ref = zo.scorer(f["point_x"], ws[o % 2])
+        best = cand[int(torch.argmax(ref))]
+        assert int(I[o, 0]) == best, f"object {o}: GPU top-1 {int(I[o, 0])} != fp32 oracle argmax {best}"
+        assert abs(float(S[o, 0]) - float(ref.max())) <= SCORE_F32_RTOL * float(ref.abs().max()) + 1e-6
+    recs = []
+    for r in range(4):
+        fs.forced_rank_world = (r, 4)
+        fs.upload(sc["img"], sc["depth"], sc["cam_K"], sc["objects"], wof)
+        recs.append(fs.run_resident(local_record=True))
+    Sm, Im, P = fs.merge_records(torch.stack(recs))
+    Sm, Im = fs._rerank(Sm, Im, P)
+    fs.forced_rank_world = None
+    assert np.array_equal(Im.cpu().numpy(), I) and np.array_equal(Sm.cpu().numpy(), S)
+
+
 def test_reference_glue_drives_the_gpu_path_when_present(ctx, golden_dir):
     """The reference's own, unmodified networkInference (python/ossid/utils/zephyr_utils.py:10-47) on top of the shim.
     Needs /root/reference AND a GPU in one place; skipped wherever either is missing (the mirror is tested above)."""
