@@ -314,7 +314,7 @@ class Runner:
             pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
             objs = [dict(model_points=pin(ob["model_points"]), model_colors=pin(ob["model_colors"]),
                          model_normals=pin(ob["model_normals"]),
-                         pose_hypos=pin(ob["pose_hypos"].astype(np.float32)),
+                         pose_hypos=pin(ob["pose_hypos"]),          # float64 (M,4,4), as the reference hands them over
                          **{k: ob[k] for k in ("boxes", "box_scores") if k in ob}) for ob in sc["objects"]]
             self.frame = dict(img=pin(sc["img"]), depth=pin(sc["depth"]), cam_K=sc["cam_K"], objects=objs)
         return self.frame
@@ -422,7 +422,8 @@ def main():
     scored = int(fs.last_scored) * n_frames if fs._plan.filtered else total_hyp
 
     # ---- end-to-end arm through the public host-buffer API: `e2e` ----------------------------------
-    # per frame: H2D of the uint8 image, the float32 depth and this rank's pose hypotheses, D2H of the top-k; the model
+    # per frame: H2D of the uint8 image, the float32 depth and this rank's pose hypotheses (float64 (M,4,4) blocks as the
+    # reference hands them over, cast to float32 rows on the device), D2H of the top-k; the model
     # clouds are static assets (the reference loads them once, online_learning.py:303-311): uploaded by the warm-up only
     run.e2e(max(5, args.warmup))                                  # warm-up frames (build the pinned cloud copies, size the rings)
     e2e_runs = []
@@ -432,7 +433,8 @@ def main():
         e2e_runs.append(max_over_ranks(sec) / args.steps)
     e2e_s = statistics.median(e2e_runs)
     frame = run.host_frame()
-    h2d = n_frames * (frame["img"].numel() + frame["depth"].numel() * 4) + local_hyp * 64
+    pose_bytes = frame["objects"][0]["pose_hypos"].element_size() * 16
+    h2d = n_frames * (frame["img"].numel() + frame["depth"].numel() * 4) + local_hyp * pose_bytes
     d2h = int(Sh.size * 4 + Ih.size * 4) * n_frames
     if not (np.array_equal(Ih, I.cpu().numpy()) and np.array_equal(Sh, S.cpu().numpy())):
         raise SystemExit("end-to-end result differs from the device-resident result")
