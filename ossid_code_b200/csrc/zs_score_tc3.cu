@@ -55,8 +55,11 @@ enum : int {
     BAR_XP_FULL = 20 /*3*/, BAR_WP_FULL = 23, BAR_COUNT = 24
 };
 
-constexpr uint32_t kColD1 = 0, kColD2 = 0, kColD3 = 128;       // D1 inside D2 (see zs_score_tc.cu), three layer-3 accumulators
-constexpr int kD3Bufs = 3;
+// D1 has its own columns here (the bf16 kernel aliases it into D2): layer 1 of pair-tile i+1 is issued right behind
+// layer 2 of pair-tile i, so its accumulator is waiting when the epilogue warps come back from H2(i) - one commit ->
+// wake-up latency less in the L1 -> H1 -> L2 -> H2 chain that bounds this kernel.  Two layer-3 accumulators remain.
+constexpr uint32_t kColD2 = 0, kColD1 = 128, kColD3 = 192;
+constexpr int kD3Bufs = 2;
 constexpr uint32_t kTmemCols = 512;
 
 // global image of the split operands (bytes): W3 [quarter][rank][term][k-half] x 16 KB, W2 [rank][term] x 8 KB,
@@ -235,24 +238,24 @@ zs_k_mlp_tc3(const uint8_t* __restrict__ feat, int n, int N, const uint8_t* __re
                 tc_commit(bar(BAR_D3_FULL + b));
                 if (hh == 1) tc_commit(bar(BAR_A3_EMPTY + buf));
             };
+            auto issue_l1 = [&](int it) {                      // [Xhi|Xlo].[W1hi|W1hi]^T + [Xhi|Xlo].[W1lo|0]^T
+                const int s = it % kStages;
+                mbar_wait(bar(BAR_X_FULL + s), (it / kStages) & 1);
+                mbar_wait(bar(BAR_XP_FULL + s), (it / kStages) & 1);
+                tc_fence_after();
+                const uint64_t xd = desc_at(desc_lo(sbase + kSmX + s * 4096, 2048), hi_x, 0);   // K 0-7 = hi plane, 8-15 = lo plane
+                tc_mma(tmem + kColD1, xd, desc_at(w1_lo, hi_x, 0), idesc_l1, 0);
+                tc_mma(tmem + kColD1, xd, desc_at(w1_lo, hi_x, 1024), idesc_l1, 1);
+                tc_commit(bar(BAR_X_EMPTY + s));
+                tc_commit(bar(BAR_D1_FULL));
+            };
+            if (total > 0) issue_l1(0);
             for (int i = 0; i <= total; ++i) {
-                // H2 of pair-tile i-1 is ready in both CTAs and D2 (which D1 aliases) has been drained by both epilogues 2
-                if (i >= 1) mbar_wait(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1);
-                if (i < total) {
-                    const int s = i % kStages;
-                    mbar_wait(bar(BAR_X_FULL + s), (i / kStages) & 1);
-                    mbar_wait(bar(BAR_XP_FULL + s), (i / kStages) & 1);
-                    tc_fence_after();
-                    const uint64_t xd = desc_at(desc_lo(sbase + kSmX + s * 4096, 2048), hi_x, 0);   // K 0-7 = hi plane, 8-15 = lo plane
-                    tc_mma(tmem + kColD1, xd, desc_at(w1_lo, hi_x, 0), idesc_l1, 0);                 // [Xhi|Xlo].[W1hi|W1hi]^T
-                    tc_mma(tmem + kColD1, xd, desc_at(w1_lo, hi_x, 1024), idesc_l1, 1);              // [Xhi|Xlo].[W1lo|0]^T
-                    tc_commit(bar(BAR_X_EMPTY + s));
-                    tc_commit(bar(BAR_D1_FULL));
-                }
-                if (i >= 1) issue_l3(i - 1, 0);
+                // H2 of pair-tile i-1 is ready in both CTAs and both epilogues 2 have drained D2
+                if (i >= 1) { mbar_wait(bar(BAR_A3_FULL + ((i - 1) & 1)), ((i - 1) >> 1) & 1); issue_l3(i - 1, 0); }
                 if (i < total) {
                     const uint32_t a2_lo = desc_lo(sbase + kSmA3 + (i & 1) * kA3Buf, 16);
-                    mbar_wait(bar(BAR_A2_FULL), i & 1);
+                    mbar_wait(bar(BAR_A2_FULL), i & 1);            // H1(i) is in place, so D1 has been read
                     tc_fence_after();
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {       // H1hi.W2hi + H1lo.W2hi + H1hi.W2lo
@@ -263,6 +266,7 @@ zs_k_mlp_tc3(const uint8_t* __restrict__ feat, int n, int N, const uint8_t* __re
                                    desc_at(w2_lo, hi_sw, tw * 8192 + kk * 32), idesc_128, (term | kk) != 0);
                     }
                     tc_commit(bar(BAR_D2_FULL));
+                    if (i + 1 < total) issue_l1(i + 1);           // early: D1 is its own TMEM range
                 }
                 if (i >= 1) issue_l3(i - 1, 1);
             }
